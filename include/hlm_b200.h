@@ -1,0 +1,169 @@
+/*
+ * hlm_b200.h — C ABI of libhlm_b200.so: batched Dormand–Prince RK45 integration of per-link
+ * runoff ODEs on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of PrincetonUniversity/Tiger_HLM_GPU: what its host
+ * code does between "per-link parameters, forcings and y0 are in host memory" and "final and
+ * dense states are back in host memory".  Each entry point names the reference interface it
+ * replaces (paths relative to the reference's src/).  Plain pointers and sizes only; no C++ types,
+ * no exceptions, no templates cross this boundary.  The header-only C++ shims in
+ * include/hlm_b200/rk45_api.hpp rebuild the reference's own operator surface
+ * (rk45_api::setModelParameters<T>(), rk45_api::run_rk45<T>(), the Model trait) on top of it.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative hlm_status; hlm_last_error() then holds
+ *     a message for the calling thread (the reference throws std::runtime_error instead,
+ *     solver/rk45_api.hpp:87-108 — the shims re-throw);
+ *   - times are in MINUTES, query times ascending (solver/rk45_kernel.cu:139);
+ *   - a context is bound to one CUDA device and is not thread-safe; create one per device
+ *     (the reference: one MPI rank per GPU and process-global __constant__ state);
+ *   - there is no CPU fallback: every entry point that computes fails with HLM_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef HLM_B200_H
+#define HLM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hlm_ctx hlm_ctx;
+
+typedef enum hlm_status {
+    HLM_OK = 0,
+    HLM_ERR_INVALID = -1, /* bad argument (null pointer, size, unknown model uid, ...) */
+    HLM_ERR_CUDA = -2,    /* CUDA runtime failure, message has the CUDA error string */
+    HLM_ERR_STATE = -3,   /* call out of order (e.g. run before parameters were uploaded) */
+    HLM_ERR_NOMEM = -4    /* host or device allocation failed */
+} hlm_status;
+
+/* Model UIDs compiled into the library.  204 is the reference's Model204::UID
+ * (models/model_204.hpp:18); 0 is the DummyModel of model_dummy_python.ipynb:65-89, to which the
+ * reference never assigned a UID. */
+#define HLM_MODEL_DUMMY 0
+#define HLM_MODEL_204 204
+
+/* per-link result codes written to out_stiff: 0 = integrated to tf; 1 = flagged stiff and
+ * abandoned, exactly the reference's d_stiff[sys] = 1 (solver/rk45_kernel.cu:160-170);
+ * 2 = attempt budget of hlm_set_max_attempts() exhausted (no reference equivalent: the reference
+ * would spin forever). */
+#define HLM_LINK_OK 0
+#define HLM_LINK_STIFF 1
+#define HLM_LINK_STALLED 2
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Bind a context to CUDA device `device`.  Replaces the per-rank cudaSetDevice of main.cpp:314-319. */
+int hlm_create(int device, hlm_ctx** out);
+void hlm_destroy(hlm_ctx* ctx);
+/* Message of the last failure on this thread ("" if none). */
+const char* hlm_last_error(void);
+/* Library/ABI version, for the loader check in the Python mirror. */
+int hlm_abi_version(void);
+/* Run all work of this context on `cuda_stream` (a cudaStream_t); NULL = the context's own stream.
+ * The reference uses the default stream and cudaDeviceSynchronize (solver/rk45_api.hpp:150). */
+int hlm_set_stream(hlm_ctx* ctx, void* cuda_stream);
+/* Block until all work queued by this context has finished. */
+int hlm_synchronize(hlm_ctx* ctx);
+
+/* ---- model registry -------------------------------------------------------------------------- */
+
+/* N_EQ, number of SoA parameter columns and number of forcings read by model `uid`.
+ * Replaces the compile-time Model::N_EQ of the trait (models/model_204.hpp:19). */
+int hlm_model_info(int uid, int* n_eq, int* n_sp, int* n_forc);
+
+/* Replaces rk45_api::setModelParameters<T>(const T::Parameters&) (model_registry.hpp:9-13,
+ * model_registry.cpp:18-60), which copies 48 bytes into __constant__ devParams.
+ * p = {initialStep, rtol, atol, safety, minScale, maxScale} (models/model_204.hpp:22-30). */
+int hlm_set_model_parameters(hlm_ctx* ctx, int uid, const double p[6]);
+int hlm_get_model_parameters(hlm_ctx* ctx, int uid, double p[6]);
+
+/* ---- per-link inputs ------------------------------------------------------------------------- */
+
+/* Replaces the cudaMalloc/cudaMemcpy of the AoS SpatialParams array (main.cpp:392-404) and, across
+ * GPUs, the MPI rank-0 scatter of its row chunks (main.cpp:269-309,357-366): the caller hands each
+ * device context its own contiguous slice.  `aos` points at `n` records `stride_bytes` apart, each
+ * laid out as the reference's 136-byte SpatialParams (I_O/parameters_loader.hpp:19-37).  The
+ * records are transposed on the device into the structure-of-arrays columns each model needs. */
+int hlm_upload_spatial_params(hlm_ctx* ctx, const void* aos, long long n, long long stride_bytes);
+
+/* Replaces the forcing side channel: d_forc_data upload plus cudaMemcpyToSymbol of c_forc_dt /
+ * c_forc_nT (main.cpp:552-574, I_O/forcing_data.h:5-13).  Forcing j (0 = precipitation, 1 = 2 m
+ * temperature for Model204) is a float array [nT][ncols], sampled with step-hold at
+ * index size_t(t / (dt_hours*60)) clamped to [0, nT-1] (solver/rk45_kernel.cu:90-98).
+ * With hlm_set_forcing_columns(NULL) column c serves link c — the reference's per-link-expanded
+ * [forcing][time][system] layout (main.cpp:543-548).  With a column map the array is the forcing
+ * GRID (ncols = lat*lon cells) and link s reads column col[s] = lat_index*lon_size + lon_index
+ * (main.cpp:501-505); the per-link expansion is never materialised. */
+int hlm_upload_forcing(hlm_ctx* ctx, int j, double dt_hours, long long nT, long long ncols, const float* data);
+int hlm_set_forcing_columns(hlm_ctx* ctx, const int* col, long long n);
+int hlm_clear_forcings(hlm_ctx* ctx);
+
+/* ---- solver options (no reference equivalent) ------------------------------------------------- */
+
+/* Attempt budget per link per window launch; <= 0 = unbounded like the reference.  Default 0. */
+int hlm_set_max_attempts(hlm_ctx* ctx, long long per_link);
+/* Bytes of device memory one dense-output window buffer may take (two are allocated when the run
+ * needs more than one window).  Default 8 GiB. */
+int hlm_set_dense_window_bytes(hlm_ctx* ctx, long long bytes);
+/* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */
+int hlm_set_precision(hlm_ctx* ctx, int bits);
+
+/* ---- the operator ---------------------------------------------------------------------------- */
+
+/* Replaces rk45_api::run_rk45<T>(h_y0, t0, tf, h_query_times, d_sp) (solver/rk45_api.hpp:273-313)
+ * = setup_gpu_buffers + launch_rk45_kernel + retrieve_and_free (solver/rk45_api.hpp:63-270), minus
+ * the Radau re-integration of flagged links (out of scope).
+ *   y0          host [ns][N_EQ]
+ *   tq          host [nq] ascending query times (may be NULL when nq == 0)
+ *   out_final   host [ns][N_EQ]; rows of links that did not reach tf are zero (the reference
+ *               leaves them unwritten, solver/rk45_kernel.cu:167-175)
+ *   out_dense   host [ns][nq][N_EQ] — the order retrieve_and_free returns
+ *               (solver/rk45_api.hpp:255-267); slots never reached (tq <= t0, or after a stiff
+ *               bail-out) are zero.  May be NULL.
+ *   out_stiff   host [ns] HLM_LINK_* codes.  May be NULL.
+ *   out_n_*     host [ns] accepted / rejected / slope-jump attempt counts.  May be NULL.
+ * ns must equal the number of uploaded SpatialParams records for models that use them. */
+int hlm_run_rk45(hlm_ctx* ctx, int uid, const double* y0, long long ns, double t0, double tf,
+                 const double* tq, long long nq, double* out_final, double* out_dense, int* out_stiff,
+                 long long* out_n_accept, long long* out_n_reject, long long* out_n_jump);
+
+/* ---- resident session: the same operator cut into output windows, state left in HBM ---------- */
+
+/* Upload y0 and the query times, reset per-link state (t = t0, h = initialStep, counters 0). */
+int hlm_solve_begin(hlm_ctx* ctx, int uid, const double* y0, long long ns, double t0, double tf,
+                    const double* tq, long long nq);
+/* Advance every unfinished link until it has emitted all queries with index < q_hi (to tf when
+ * q_hi >= nq).  Dense records of queries [previous q_hi, q_hi) go to a device buffer
+ * [ns][q_hi - q_lo][N_EQ] owned by the context (skipped when want_dense == 0).  Asynchronous. */
+int hlm_solve_window(hlm_ctx* ctx, long long q_hi, int want_dense);
+/* Device pointer, query range and row pitch of the last window's dense buffer. */
+int hlm_solve_window_buffer(hlm_ctx* ctx, void** dev_ptr, long long* q_lo, long long* q_hi);
+/* Copy the last window's dense records into the full host array [ns][nq][N_EQ]. Asynchronous if
+ * `host_dense` is pinned. */
+int hlm_solve_fetch_window(hlm_ctx* ctx, double* host_dense);
+/* Sums over links, computed on the device: {accepted, rejected, slope-jump, unfinished-active,
+ * done, stiff, stalled}.  Synchronises. */
+int hlm_solve_totals(hlm_ctx* ctx, long long totals[7]);
+/* Download final states and per-link codes/counters (any pointer may be NULL).  Synchronises. */
+int hlm_solve_end(hlm_ctx* ctx, double* out_final, int* out_stiff, long long* out_n_accept,
+                  long long* out_n_reject, long long* out_n_jump);
+/* Download the raw resident state (t, h per link) for inspection/tests.  Either may be NULL. */
+int hlm_solve_peek(hlm_ctx* ctx, double* out_t, double* out_h, double* out_y);
+/* Number of kernel launches issued by this context since creation (bench's gpu_launches). */
+long long hlm_launch_count(hlm_ctx* ctx);
+/* CUDA-event time, in ms, of the window kernels launched since the last call (sum), and how many.
+ * Synchronises the context's stream. */
+int hlm_kernel_time_ms(hlm_ctx* ctx, double* sum_ms, long long* n_launches);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+
+/* Register-resident DFMA / FFMA microbenchmark: achieved FMA throughput of this device in
+ * TFLOP/s (2 flops per FMA).  Used as the roofline denominator, which MEASURED_PEAKS.json lacks
+ * for FP64/FP32. bits = 64 or 32. */
+int hlm_measure_fma_peak(hlm_ctx* ctx, int bits, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HLM_B200_H */

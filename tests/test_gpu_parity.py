@@ -1,0 +1,319 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden vectors.
+
+Bar (north star): FP64 final and dense states within the solver's own tolerance — and, here,
+BIT FOR BIT wherever pow() is not exercised (h_surf == 0), because every other operation is IEEE
+correctly rounded on both sides and the contraction pattern is pinned (fp_exact.cuh).  Accepted /
+rejected / slope-jump counts must be exactly equal.  Where Model204's pow(h_surf, 2/3) runs, glibc
+and CUDA libdevice may differ in the last bit, so states are compared at 1e-11 relative and counts
+are still required to be equal (the bit-for-bit pin for that branch is the unchanged reference
+kernel, tests/test_gpu_reference_cuda.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tiger_hlm_gpu_b200 import Parameters, synthetic
+
+pytestmark = pytest.mark.gpu
+
+PRM = Parameters(initialStep=1e-6)  # main.cpp:633-640
+OPRM = O.Params.make(initialStep=1e-6)
+
+
+def assert_same_result(g, o, exact=True, rtol=1e-11):
+    assert np.array_equal(g["stiff"], o["stiff"])
+    assert np.array_equal(g["n_accept"], o["n_accept"])
+    assert np.array_equal(g["n_reject"], o["n_reject"])
+    assert np.array_equal(g["n_jump"], o["n_jump"])
+    if exact:
+        assert np.array_equal(g["final"], o["final"])
+        if o.get("dense") is not None and g.get("dense") is not None:
+            assert np.array_equal(g["dense"], o["dense"])
+    else:
+        np.testing.assert_allclose(g["final"], o["final"], rtol=rtol, atol=1e-300)
+        if o.get("dense") is not None and g.get("dense") is not None:
+            np.testing.assert_allclose(g["dense"], o["dense"], rtol=rtol, atol=1e-300)
+
+
+def setup_synth(solver, ns, days, wet_fraction=0.0, grid=True):
+    sp = synthetic.make_spatial_params(ns)
+    col, ncells = synthetic.make_cells(ns, links_per_cell=97)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days)
+    y0 = synthetic.make_y0(ns, wet_fraction)
+    solver.set_model_parameters(204, PRM)
+    solver.set_max_attempts(2_000_000)
+    solver.upload_spatial_params(sp)
+    solver.clear_forcings()
+    if grid:
+        solver.upload_forcing(0, 1.0, pr)
+        solver.upload_forcing(1, 24.0, t2m)
+        solver.set_forcing_columns(col)
+    else:
+        solver.upload_forcing(0, 1.0, synthetic.expand_forcing_per_link(pr, col))
+        solver.upload_forcing(1, 24.0, synthetic.expand_forcing_per_link(t2m, col))
+        solver.set_forcing_columns(None)
+    forcing = O.Forcing([pr, t2m], [1.0, 24.0], col=col)
+    return sp, y0, forcing
+
+
+# ---- golden vectors --------------------------------------------------------------------------------
+
+def test_model204_golden_example(solver, small_test_params, golden204):
+    """C2: 10 links of data/small_test.csv, constant forcing, 2881 queries (src/*_example.nc)."""
+    sp = small_test_params
+    ns = len(sp)
+    y0 = np.tile(synthetic.Y0_204, (ns, 1))
+    tq = golden204["query_times"]
+    solver.set_model_parameters(204, PRM)
+    solver.set_max_attempts(100000)
+    solver.upload_spatial_params(sp)
+    solver.clear_forcings()
+    # the golden used double literals 0.001 / 1.0; the operator takes float forcings (model_204.hpp:82-83)
+    pr = np.full((48, ns), 0.001, np.float32)
+    t2m = np.full((2, ns), 1.0, np.float32)
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(None)
+    g = solver.run_rk45(204, y0, 0.0, 2880.0, tq)
+    o = O.run_rk45(204, OPRM, y0, 0.0, 2880.0, tq, sp=sp, forcing=O.Forcing([pr, t2m], [1.0, 24.0]))
+    assert_same_result(g, o, exact=True)
+    # against the reference's own output: float(0.001) vs the double literal shifts the snow store by
+    # 4.7e-8 relative, well inside the solver tolerance
+    tol = 10 * (1e-9 + 1e-6 * np.abs(golden204["final"]))
+    assert np.all(np.abs(g["final"] - golden204["final"]) <= tol)
+    gd = golden204["dense_sys0"]
+    assert np.all(np.abs(g["dense"] - gd[None]) <= 10 * (1e-9 + 1e-6 * np.abs(gd[None])))
+    assert np.all(g["dense"][:, 0, :] == 0.0)  # tq == t0 is never written
+
+
+def test_dummy_golden(solver, golden_dummy):
+    """C1: DummyModel, y0 = ones, t in [0,5], 10 000 queries (src/final.csv, src/dense.csv)."""
+    tq = golden_dummy["query_times"]
+    solver.set_model_parameters(0, Parameters())
+    solver.set_max_attempts(100000)
+    y0 = np.ones((4, 5))
+    g = solver.run_rk45(0, y0, 0.0, 5.0, tq)
+    o = O.run_rk45(0, O.Params.make(), y0, 0.0, 5.0, tq)
+    assert_same_result(g, o, exact=True)
+    np.testing.assert_allclose(g["final"], golden_dummy["final_csv"], rtol=3e-6)
+    np.testing.assert_allclose(g["dense"][0], golden_dummy["dense_csv_sys0"], rtol=2e-5, atol=1e-6)
+    tol = 10 * (1e-9 + 1e-6 * np.abs(golden_dummy["scipy_final"]))
+    assert np.all(np.abs(g["final"][0] - golden_dummy["scipy_final"]) < tol)
+
+
+# ---- seeded synthetic inputs -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("ns,days", [(1, 2), (31, 2), (33, 2), (1000, 3)])
+def test_synthetic_dry_bit_exact(solver, ns, days):
+    sp, y0, forcing = setup_synth(solver, ns, days)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    g = solver.run_rk45(204, y0, 0.0, tf, tq)
+    o = O.run_rk45(204, OPRM, y0, 0.0, tf, tq, sp=sp, forcing=forcing, threads=8)
+    assert g["n_accept"].min() > 100 * days
+    assert_same_result(g, o, exact=True)
+
+
+def test_synthetic_wet_counts_exact_states_tight(solver):
+    ns, days = 600, 2
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.5)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    g = solver.run_rk45(204, y0, 0.0, tf, tq)
+    o = O.run_rk45(204, OPRM, y0, 0.0, tf, tq, sp=sp, forcing=forcing, threads=8)
+    assert (y0[:, 2] > 0).sum() > 100
+    assert_same_result(g, o, exact=False, rtol=1e-11)
+    dry = y0[:, 2] == 0
+    assert np.array_equal(g["final"][dry], o["final"][dry])
+
+
+def test_grid_forcing_equals_per_link_expanded_forcing(solver):
+    """The grid + column map is the same operator as the reference's per-link expansion (main.cpp:543-548)."""
+    ns, days = 500, 2
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    _, y0, _ = setup_synth(solver, ns, days, grid=True)
+    a = solver.run_rk45(204, y0, 0.0, tf, tq)
+    setup_synth(solver, ns, days, grid=False)
+    b = solver.run_rk45(204, y0, 0.0, tf, tq)
+    assert_same_result(a, b, exact=True)
+
+
+def test_windowed_run_is_bit_identical_to_single_window(solver):
+    """Cutting the run into query windows must not change a single bit or count (no clipping of h)."""
+    ns, days = 300, 3
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.3)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    solver.set_dense_window_bytes(8 << 30)
+    a = solver.run_rk45(204, y0, 0.0, tf, tq)
+    solver.set_dense_window_bytes(ns * 5 * 8 * 7)  # 7 queries per window -> 11 windows
+    n0 = solver.launch_count()
+    b = solver.run_rk45(204, y0, 0.0, tf, tq)
+    assert solver.launch_count() - n0 >= 11
+    solver.set_dense_window_bytes(ns * 5 * 8)      # 1 query per window
+    c = solver.run_rk45(204, y0, 0.0, tf, tq)
+    solver.set_dense_window_bytes(8 << 30)
+    assert_same_result(a, b, exact=True)
+    assert_same_result(a, c, exact=True)
+
+
+def test_windows_with_steps_longer_than_the_query_spacing(solver, golden_dummy):
+    """DummyModel takes 12 steps for 10 000 queries: every window boundary falls inside a step, which
+    exercises the leave-uncommitted-and-redo path."""
+    tq = golden_dummy["query_times"]
+    solver.set_model_parameters(0, Parameters())
+    y0 = np.ones((40, 5)) * np.linspace(0.5, 1.5, 40)[:, None]
+    a = solver.run_rk45(0, y0, 0.0, 5.0, tq)
+    solver.set_dense_window_bytes(40 * 5 * 8 * 333)
+    b = solver.run_rk45(0, y0, 0.0, 5.0, tq)
+    solver.set_dense_window_bytes(8 << 30)
+    assert_same_result(a, b, exact=True)
+    o = O.run_rk45(0, O.Params.make(), y0, 0.0, 5.0, tq)
+    assert_same_result(a, o, exact=True)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+
+def test_no_queries_and_final_only(solver):
+    ns, days = 200, 1
+    sp, y0, forcing = setup_synth(solver, ns, days)
+    tf = 1440.0
+    g = solver.run_rk45(204, y0, 0.0, tf, None)
+    o = O.run_rk45(204, OPRM, y0, 0.0, tf, np.zeros(0), sp=sp, forcing=forcing)
+    assert g["dense"] is None
+    assert_same_result(g, o, exact=True)
+    tq = synthetic.hourly_queries(0.0, tf)
+    g2 = solver.run_rk45(204, y0, 0.0, tf, tq, want_dense=False)
+    assert np.array_equal(g2["final"], g["final"]) and np.array_equal(g2["n_accept"], g["n_accept"])
+
+
+def test_queries_outside_the_interval(solver):
+    """tq <= t0 slots stay zero (F10); tq > tf slots are never reached."""
+    ns = 64
+    sp, y0, forcing = setup_synth(solver, ns, 1)
+    tq = np.array([-5.0, 0.0, 1e-3, 30.0, 600.0, 1440.0, 1440.0 + 1e-9, 2000.0])
+    g = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
+    o = O.run_rk45(204, OPRM, y0, 0.0, 1440.0, tq, sp=sp, forcing=forcing)
+    assert_same_result(g, o, exact=True)
+    assert np.all(g["dense"][:, :2] == 0) and np.all(g["dense"][:, 6:] == 0) and np.all(g["dense"][:, 2:6, 1] != 0)
+
+
+def test_empty_interval(solver):
+    ns = 40
+    sp, y0, forcing = setup_synth(solver, ns, 1)
+    g = solver.run_rk45(204, y0, 10.0, 10.0, np.array([10.0, 11.0]))
+    assert np.array_equal(g["final"], y0) and not g["n_accept"].any() and not g["stiff"].any()
+    assert np.all(g["dense"] == 0)
+
+
+def test_stiff_flag_matches_reference_semantics(solver):
+    """Raw-unit rain (the reference feeds pr unscaled) drives links stiff; flagged links
+    report no final state and the same flags/counters as the oracle."""
+    ns, days = 128, 2
+    sp = synthetic.make_spatial_params(ns)
+    col, ncells = synthetic.make_cells(ns, links_per_cell=16)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days)
+    pr = (pr / synthetic.C1).astype(np.float32)  # back to mm/h magnitudes, i.e. 6e4 x too large
+    y0 = synthetic.make_y0(ns)
+    solver.set_model_parameters(204, PRM)
+    solver.upload_spatial_params(sp)
+    solver.clear_forcings()
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(col)
+    tf = days * 1440.0 * 15  # long horizon raises the min-step threshold (tf - t0)*1e-6
+    tq = synthetic.hourly_queries(0.0, 2880.0)
+    g = solver.run_rk45(204, y0, 0.0, tf, tq)
+    o = O.run_rk45(204, OPRM, y0, 0.0, tf, tq, sp=sp, forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col), threads=8)
+    assert o["stiff"].sum() > 0, "test input should drive some links stiff"
+    assert_same_result(g, o, exact=False, rtol=1e-11)
+    assert np.all(g["final"][g["stiff"] == 1] == 0.0)
+
+
+def test_attempt_budget_reports_stalled(solver):
+    ns = 32
+    sp, y0, forcing = setup_synth(solver, ns, 1)
+    solver.set_max_attempts(50)
+    g = solver.run_rk45(204, y0, 0.0, 1440.0, None)
+    solver.set_max_attempts(2_000_000)
+    assert np.all(g["stiff"] == 2) and np.all(g["n_accept"] + g["n_reject"] + g["n_jump"] == 50)
+    assert np.all(g["final"] == 0)
+
+
+def test_errors_are_loud(solver):
+    from tiger_hlm_gpu_b200 import HlmError
+    with pytest.raises(HlmError, match="unknown model uid"):
+        solver.set_model_parameters(200, Parameters())
+    with pytest.raises(HlmError, match="unknown model uid"):
+        solver.run_rk45(200, np.ones((4, 5)), 0.0, 1.0, None)
+    solver.upload_spatial_params(synthetic.make_spatial_params(10))
+    with pytest.raises(HlmError, match="exactly ns SpatialParams"):
+        solver.run_rk45(204, np.ones((11, 5)), 0.0, 1.0, None)
+
+
+# ---- resident session, partition invariance, FP32 ---------------------------------------------------
+
+def test_session_windows_and_totals(solver):
+    ns, days = 257, 2
+    sp, y0, forcing = setup_synth(solver, ns, days)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    full = solver.run_rk45(204, y0, 0.0, tf, tq)
+    solver.solve_begin(204, y0, 0.0, tf, tq)
+    dense = np.zeros((ns, len(tq), 5))
+    for q in (10, 25, 48, len(tq)):
+        solver.solve_window(q)
+        solver.solve_fetch_window(dense)
+    tot = solver.solve_totals()
+    r = solver.solve_end()
+    assert np.array_equal(dense, full["dense"]) and np.array_equal(r["final"], full["final"])
+    assert tot["n_accept"] == full["n_accept"].sum() and tot["n_reject"] == full["n_reject"].sum()
+    assert tot["done"] == ns and tot["active"] == 0 and tot["stiff"] == 0
+
+
+def test_partition_invariance(solver):
+    """Sharding links over devices = running disjoint slices; per-link results must not depend on it."""
+    ns, days = 400, 2
+    sp = synthetic.make_spatial_params(ns)
+    col, ncells = synthetic.make_cells(ns, links_per_cell=97)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days)
+    y0 = synthetic.make_y0(ns, 0.25)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    solver.set_model_parameters(204, PRM)
+    solver.clear_forcings()
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+
+    def run(lo, hi):
+        solver.upload_spatial_params(sp[lo:hi])
+        solver.set_forcing_columns(col[lo:hi])
+        return solver.run_rk45(204, y0[lo:hi], 0.0, tf, tq)
+
+    whole = run(0, ns)
+    for cuts in ([0, 200, 400], [0, 100, 200, 300, 400], [0, 57, 400]):
+        parts = [run(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+        for key in ("final", "dense", "n_accept", "n_reject", "n_jump", "stiff"):
+            assert np.array_equal(np.concatenate([p[key] for p in parts]), whole[key])
+
+
+def test_fp32_mode_tracks_fp64(solver):
+    """FP32 has no reference counterpart; it must stay within a stated looser tolerance of FP64."""
+    ns, days = 256, 1
+    sp, y0, forcing = setup_synth(solver, ns, days)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    solver.set_model_parameters(204, Parameters(initialStep=1e-4, rtol=1e-4, atol=1e-7))
+    d = solver.run_rk45(204, y0, 0.0, tf, tq)
+    solver.set_precision(32)
+    try:
+        s = solver.run_rk45(204, y0, 0.0, tf, tq)
+    finally:
+        solver.set_precision(64)
+        solver.set_model_parameters(204, PRM)
+    assert not s["stiff"].any()
+    np.testing.assert_allclose(s["final"], d["final"], rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(s["dense"], d["dense"], rtol=2e-3, atol=2e-6)

@@ -1,0 +1,746 @@
+// hlm_capi.cu — the C ABI of include/hlm_b200.h over the kernels in rk45_window.cuh.
+//
+// Host side of the operator: what the reference spreads over setup_gpu_buffers /
+// launch_rk45_kernel / retrieve_and_free (solver/rk45_api.hpp:63-270), setModelParameters
+// (model_registry.cpp:18-60) and the upload code in main.cpp:392-404,552-574.  Differences by
+// design: buffers are owned by a context and re-used across calls (the reference allocates and
+// frees five buffers per call), everything runs on one stream without device-wide synchronisation,
+// results land directly in the caller's [link][query][state] layout, and long runs are cut into
+// query windows whose D2H copy overlaps the next window's integration.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hlm_b200.h"
+#include "rk45_window.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define HLM_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(HLM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+#define HLM_REQUIRE(cond, msg)                            \
+    do {                                                  \
+        if (!(cond)) return fail(HLM_ERR_INVALID, (msg)); \
+    } while (0)
+
+// device buffer that grows but never shrinks
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct ModelInfo {
+    int uid, n_eq, n_sp, n_forc;
+};
+const ModelInfo kModels[] = {
+    {hlm::DummyModel::UID, hlm::DummyModel::N_EQ, hlm::DummyModel::N_SP, hlm::DummyModel::N_FORC},
+    {hlm::Model204::UID, hlm::Model204::N_EQ, hlm::Model204::N_SP, hlm::Model204::N_FORC},
+};
+const ModelInfo* find_model(int uid) {
+    for (const auto& m : kModels)
+        if (m.uid == uid) return &m;
+    return nullptr;
+}
+
+}  // namespace
+
+struct hlm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;   // compute
+    cudaStream_t stream = nullptr;       // = own_stream or the caller's
+    cudaStream_t copy_stream = nullptr;  // D2H of finished windows
+    std::map<int, hlm::SolverParams> params;
+    long long max_attempts = 0;
+    long long dense_window_bytes = 8LL << 30;
+    int precision = 64;
+
+    // per-link parameters (AoS copy kept on device so any model can be prepared lazily)
+    DevBuf<unsigned char> sp_aos;
+    long long sp_n = 0;
+    DevBuf<double> sp_soa;
+    int sp_soa_uid = -1;
+    long long sp_soa_ld = 0;
+
+    // forcings
+    DevBuf<float> forc[2];
+    long long forc_nT[2] = {0, 0};
+    long long forc_ncols = 0;
+    double forc_dt_h[2] = {0, 0};
+    int n_forc = 0;
+    DevBuf<int> forc_col;
+    long long forc_col_n = 0;  // 0 = identity
+
+    // session
+    bool in_session = false;
+    int uid = -1;
+    int n_eq = 0;
+    long long ns = 0, ld = 0, nq = 0;
+    double t0 = 0, tf = 0;
+    long long q_done = 0;  // queries [0, q_done) have been emitted
+    DevBuf<double> y, t, h, tq;
+    DevBuf<int> next_q, reject_run, status;
+    DevBuf<unsigned int> n_acc, n_rej, n_jump, tile_counter;
+    DevBuf<unsigned long long> totals;
+    DevBuf<double> dense[2];
+    int dense_cur = 0;
+    long long win_q_lo = 0, win_q_hi = 0;
+    bool win_has_dense = false;
+    cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+
+    long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // per window kernel
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+int use_device(hlm_ctx* c) {
+    HLM_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+// ---- kernels that are not the hot path -----------------------------------------------------------
+
+template <class Model>
+__global__ void prepare_params_kernel(const unsigned char* __restrict__ aos, long long n, long long stride,
+                                      double* __restrict__ soa, long long ld) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    double out[Model::N_SP > 0 ? Model::N_SP : 1];
+    if (i < n) {
+        hlm::SpatialParamsAoS rec;
+        const double* src = reinterpret_cast<const double*>(aos + i * stride);  // 8-byte aligned records
+        double* dst = reinterpret_cast<double*>(&rec);
+#pragma unroll
+        for (int w = 0; w < 17; ++w) dst[w] = src[w];
+        Model::prepare(rec, out);
+    } else {
+        for (int c = 0; c < Model::N_SP; ++c) out[c] = 1.0;  // padding lanes are never integrated
+    }
+    for (int c = 0; c < Model::N_SP; ++c) soa[(long long)c * ld + i] = out[c];
+}
+
+__global__ void init_state_kernel(const double* __restrict__ y0_aos, int n_eq, long long ns, long long ld,
+                                  double* __restrict__ y, double* __restrict__ t, double* __restrict__ h,
+                                  int* next_q, int* reject_run, int* status, unsigned int* n_acc,
+                                  unsigned int* n_rej, unsigned int* n_jump, double t0, double h0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    const bool live = i < ns;
+    for (int c = 0; c < n_eq; ++c) y[(long long)c * ld + i] = live ? y0_aos[i * n_eq + c] : 0.0;
+    t[i] = t0;
+    h[i] = h0;
+    next_q[i] = 0;
+    reject_run[i] = 0;
+    status[i] = live ? hlm::kActive : hlm::kDone;
+    n_acc[i] = n_rej[i] = n_jump[i] = 0u;
+}
+
+// final states back to the caller's [link][state] order; unfinished links give zeros
+__global__ void gather_final_kernel(const double* __restrict__ y, const int* __restrict__ status, int n_eq,
+                                    long long ns, long long ld, double* __restrict__ out_aos) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const bool ok = status[i] == hlm::kDone;
+    for (int c = 0; c < n_eq; ++c) out_aos[i * n_eq + c] = ok ? y[(long long)c * ld + i] : 0.0;
+}
+
+__global__ void totals_kernel(const unsigned int* __restrict__ n_acc, const unsigned int* __restrict__ n_rej,
+                              const unsigned int* __restrict__ n_jump, const int* __restrict__ status,
+                              long long ns, unsigned long long* __restrict__ out) {
+    unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ns;
+         i += (long long)gridDim.x * blockDim.x) {
+        v[0] += n_acc[i];
+        v[1] += n_rej[i];
+        v[2] += n_jump[i];
+        const int s = status[i];
+        v[3 + (s < 0 || s > 3 ? 0 : s)] += 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned long long x = v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);
+    }
+}
+
+// Register-resident FMA throughput probe: 8 independent chains per thread.
+template <typename T> __global__ void fma_peak_kernel(T* out, int iters, T seed) {
+    T a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+      a7 = seed + 7;
+    const T m = (T)0.999999, c = (T)1e-6;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = hlm::fp<T>::fma(a0, m, c); a1 = hlm::fp<T>::fma(a1, m, c);
+            a2 = hlm::fp<T>::fma(a2, m, c); a3 = hlm::fp<T>::fma(a3, m, c);
+            a4 = hlm::fp<T>::fma(a4, m, c); a5 = hlm::fp<T>::fma(a5, m, c);
+            a6 = hlm::fp<T>::fma(a6, m, c); a7 = hlm::fp<T>::fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <class Model> int prepare_params(hlm_ctx* c) {
+    const long long ld = c->ld;
+    if (Model::N_SP == 0) return 0;
+    if (c->sp_n != c->ns)
+        return fail(HLM_ERR_STATE, "model needs per-link parameters: upload exactly ns SpatialParams records first");
+    if (c->sp_soa_uid == Model::UID && c->sp_soa_ld == ld) return 0;
+    HLM_CUDA(c->sp_soa.reserve((size_t)Model::N_SP * ld));
+    const int tpb = 256;
+    prepare_params_kernel<Model><<<(unsigned)((ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+        c->sp_aos.p, c->sp_n, (long long)sizeof(hlm::SpatialParamsAoS), c->sp_soa.p, ld);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    c->sp_soa_uid = Model::UID;
+    c->sp_soa_ld = ld;
+    return 0;
+}
+
+cudaEvent_t get_event(hlm_ctx* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hlm::rk45_window_kernel<Model, T>, 128, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const long long n_tiles = (a.ns + 31) / 32;
+    long long grid = std::min<long long>((n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm);
+    if (grid < 1) grid = 1;
+    HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
+    cudaEvent_t e0 = get_event(c), e1 = get_event(c);
+    HLM_CUDA(cudaEventRecord(e0, c->stream));
+    hlm::rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
+    HLM_CUDA(cudaGetLastError());
+    HLM_CUDA(cudaEventRecord(e1, c->stream));
+    c->timing.emplace_back(e0, e1);
+    ++c->launches;
+    return 0;
+}
+
+int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
+    if (c->uid == hlm::Model204::UID)
+        return c->precision == 32 ? launch_window<hlm::Model204, float>(c, a) : launch_window<hlm::Model204, double>(c, a);
+    if (c->uid == hlm::DummyModel::UID)
+        return c->precision == 32 ? launch_window<hlm::DummyModel, float>(c, a)
+                                  : launch_window<hlm::DummyModel, double>(c, a);
+    return fail(HLM_ERR_INVALID, "unknown model uid");
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int hlm_abi_version(void) { return 1; }
+
+const char* hlm_last_error(void) { return g_err.c_str(); }
+
+int hlm_create(int device, hlm_ctx** out) {
+    HLM_REQUIRE(out != nullptr, "hlm_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    HLM_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(HLM_ERR_INVALID, "hlm_create: no such CUDA device");
+    HLM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HLM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(HLM_ERR_CUDA, std::string("hlm_create: device '") + prop.name +
+                                      "' is not sm_100-class; this library ships sm_100a code only and has no fallback");
+    hlm_ctx* c = new (std::nothrow) hlm_ctx();
+    if (!c) return fail(HLM_ERR_NOMEM, "hlm_create: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_kernel_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        hlm_destroy(c);
+        return fail(HLM_ERR_CUDA, std::string("hlm_create: ") + cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    // reference defaults, models/model_204.hpp:22-30
+    const hlm::SolverParams def = {0.01, 1e-6, 1e-9, 0.9, 0.2, 10.0};
+    for (const auto& m : kModels) c->params[m.uid] = def;
+    *out = c;
+    return HLM_OK;
+}
+
+void hlm_destroy(hlm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->sp_aos.release(); c->sp_soa.release(); c->forc[0].release(); c->forc[1].release(); c->forc_col.release();
+    c->y.release(); c->t.release(); c->h.release(); c->tq.release(); c->next_q.release(); c->reject_run.release();
+    c->status.release(); c->n_acc.release(); c->n_rej.release(); c->n_jump.release(); c->tile_counter.release();
+    c->totals.release(); c->dense[0].release(); c->dense[1].release();
+    for (auto& p : c->timing) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_kernel_done[i]) cudaEventDestroy(c->ev_kernel_done[i]);
+        if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int hlm_set_stream(hlm_ctx* c, void* s) {
+    HLM_REQUIRE(c, "hlm_set_stream: ctx is NULL");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return HLM_OK;
+}
+
+int hlm_synchronize(hlm_ctx* c) {
+    HLM_REQUIRE(c, "hlm_synchronize: ctx is NULL");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return HLM_OK;
+}
+
+int hlm_model_info(int uid, int* n_eq, int* n_sp, int* n_forc) {
+    const ModelInfo* m = find_model(uid);
+    if (!m) return fail(HLM_ERR_INVALID, "hlm_model_info: unknown model uid " + std::to_string(uid));
+    if (n_eq) *n_eq = m->n_eq;
+    if (n_sp) *n_sp = m->n_sp;
+    if (n_forc) *n_forc = m->n_forc;
+    return HLM_OK;
+}
+
+int hlm_set_model_parameters(hlm_ctx* c, int uid, const double p[6]) {
+    HLM_REQUIRE(c && p, "hlm_set_model_parameters: NULL argument");
+    if (!find_model(uid)) return fail(HLM_ERR_INVALID, "hlm_set_model_parameters: unknown model uid " + std::to_string(uid));
+    c->params[uid] = hlm::SolverParams{p[0], p[1], p[2], p[3], p[4], p[5]};
+    return HLM_OK;
+}
+
+int hlm_get_model_parameters(hlm_ctx* c, int uid, double p[6]) {
+    HLM_REQUIRE(c && p, "hlm_get_model_parameters: NULL argument");
+    auto it = c->params.find(uid);
+    if (it == c->params.end()) return fail(HLM_ERR_INVALID, "hlm_get_model_parameters: unknown model uid");
+    const hlm::SolverParams& s = it->second;
+    p[0] = s.initialStep; p[1] = s.rtol; p[2] = s.atol; p[3] = s.safety; p[4] = s.minScale; p[5] = s.maxScale;
+    return HLM_OK;
+}
+
+int hlm_upload_spatial_params(hlm_ctx* c, const void* aos, long long n, long long stride) {
+    HLM_REQUIRE(c, "hlm_upload_spatial_params: ctx is NULL");
+    HLM_REQUIRE(n >= 0 && (n == 0 || aos), "hlm_upload_spatial_params: NULL records");
+    HLM_REQUIRE(stride >= (long long)sizeof(hlm::SpatialParamsAoS) && stride % 8 == 0,
+                "hlm_upload_spatial_params: stride must be >= 136 and a multiple of 8");
+    if (int r = use_device(c)) return r;
+    const size_t rec = sizeof(hlm::SpatialParamsAoS);
+    HLM_CUDA(c->sp_aos.reserve((size_t)std::max<long long>(n, 1) * rec));
+    if (n > 0)
+        HLM_CUDA(cudaMemcpy2DAsync(c->sp_aos.p, rec, aos, (size_t)stride, rec, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->sp_n = n;
+    c->sp_soa_uid = -1;  // columns are rebuilt on the next solve
+    return HLM_OK;
+}
+
+int hlm_upload_forcing(hlm_ctx* c, int j, double dt_hours, long long nT, long long ncols, const float* data) {
+    HLM_REQUIRE(c && data, "hlm_upload_forcing: NULL argument");
+    HLM_REQUIRE(j >= 0 && j < hlm::kMaxForcings, "hlm_upload_forcing: forcing index out of range [0,16)");
+    HLM_REQUIRE(nT > 0 && ncols > 0, "hlm_upload_forcing: nT and ncols must be positive");
+    if (j >= 2) return HLM_OK;  // accepted like the reference's 16 slots, but no compiled model reads F[j>=2]
+    HLM_REQUIRE(j <= c->n_forc, "hlm_upload_forcing: upload forcings in order 0,1,...");
+    for (int k = 0; k < c->n_forc; ++k)
+        if (k != j && c->forc_ncols != ncols)
+            return fail(HLM_ERR_INVALID, "hlm_upload_forcing: all forcings must share ncols");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(c->forc[j].reserve((size_t)nT * ncols));
+    HLM_CUDA(cudaMemcpyAsync(c->forc[j].p, data, sizeof(float) * (size_t)nT * ncols, cudaMemcpyHostToDevice, c->stream));
+    c->forc_nT[j] = nT;
+    c->forc_dt_h[j] = dt_hours;
+    c->forc_ncols = ncols;
+    if (j == c->n_forc) c->n_forc = j + 1;
+    return HLM_OK;
+}
+
+int hlm_set_forcing_columns(hlm_ctx* c, const int* col, long long n) {
+    HLM_REQUIRE(c, "hlm_set_forcing_columns: ctx is NULL");
+    if (!col || n == 0) { c->forc_col_n = 0; return HLM_OK; }
+    if (int r = use_device(c)) return r;
+    const long long ld = (n + 31) / 32 * 32;
+    HLM_CUDA(c->forc_col.reserve((size_t)ld));
+    HLM_CUDA(cudaMemsetAsync(c->forc_col.p, 0, sizeof(int) * (size_t)ld, c->stream));
+    HLM_CUDA(cudaMemcpyAsync(c->forc_col.p, col, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->forc_col_n = n;
+    return HLM_OK;
+}
+
+int hlm_clear_forcings(hlm_ctx* c) {
+    HLM_REQUIRE(c, "hlm_clear_forcings: ctx is NULL");
+    c->n_forc = 0;
+    c->forc_col_n = 0;
+    c->forc_ncols = 0;
+    return HLM_OK;
+}
+
+int hlm_set_max_attempts(hlm_ctx* c, long long v) {
+    HLM_REQUIRE(c, "hlm_set_max_attempts: ctx is NULL");
+    c->max_attempts = v;
+    return HLM_OK;
+}
+
+int hlm_set_dense_window_bytes(hlm_ctx* c, long long v) {
+    HLM_REQUIRE(c && v > 0, "hlm_set_dense_window_bytes: need a positive size");
+    c->dense_window_bytes = v;
+    return HLM_OK;
+}
+
+int hlm_set_precision(hlm_ctx* c, int bits) {
+    HLM_REQUIRE(c && (bits == 64 || bits == 32), "hlm_set_precision: bits must be 64 or 32");
+    c->precision = bits;
+    return HLM_OK;
+}
+
+long long hlm_launch_count(hlm_ctx* c) { return c ? c->launches : 0; }
+
+int hlm_kernel_time_ms(hlm_ctx* c, double* sum_ms, long long* n) {
+    HLM_REQUIRE(c, "hlm_kernel_time_ms: ctx is NULL");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    double s = 0;
+    for (auto& p : c->timing) {
+        float ms = 0;
+        HLM_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        s += ms;
+        c->event_pool.push_back(p.first);
+        c->event_pool.push_back(p.second);
+    }
+    if (sum_ms) *sum_ms = s;
+    if (n) *n = (long long)c->timing.size();
+    c->timing.clear();
+    return HLM_OK;
+}
+
+// ---- session ------------------------------------------------------------------------------------
+
+int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
+                    long long nq) {
+    HLM_REQUIRE(c, "hlm_solve_begin: ctx is NULL");
+    const ModelInfo* m = find_model(uid);
+    if (!m) return fail(HLM_ERR_INVALID, "hlm_solve_begin: unknown model uid " + std::to_string(uid));
+    HLM_REQUIRE(ns > 0 && y0, "hlm_solve_begin: need ns > 0 and y0");
+    HLM_REQUIRE(ns < (1LL << 31) - 64, "hlm_solve_begin: ns must be below 2^31 per context");
+    HLM_REQUIRE(nq >= 0 && nq < (1LL << 31) && (nq == 0 || tq), "hlm_solve_begin: bad query times");
+    if (m->n_forc > 0 && c->n_forc > 0 && c->forc_col_n == 0 && c->forc_ncols < ns)
+        return fail(HLM_ERR_INVALID, "hlm_solve_begin: forcing has fewer columns than links and no column map");
+    if (m->n_forc > 0 && c->forc_col_n != 0 && c->forc_col_n != ns)
+        return fail(HLM_ERR_INVALID, "hlm_solve_begin: forcing column map length differs from ns");
+    if (int r = use_device(c)) return r;
+    // a previous call's D2H copies may still read the window buffers
+    HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;
+    c->in_session = false;
+    c->uid = uid;
+    c->n_eq = m->n_eq;
+    c->ns = ns;
+    c->ld = (ns + 31) / 32 * 32;
+    c->nq = nq;
+    c->t0 = t0;
+    c->tf = tf;
+    c->q_done = 0;
+    c->win_q_lo = c->win_q_hi = 0;
+    c->win_has_dense = false;
+    const size_t ld = (size_t)c->ld;
+    HLM_CUDA(c->y.reserve(ld * m->n_eq));
+    HLM_CUDA(c->t.reserve(ld));
+    HLM_CUDA(c->h.reserve(ld));
+    HLM_CUDA(c->next_q.reserve(ld));
+    HLM_CUDA(c->reject_run.reserve(ld));
+    HLM_CUDA(c->status.reserve(ld));
+    HLM_CUDA(c->n_acc.reserve(ld));
+    HLM_CUDA(c->n_rej.reserve(ld));
+    HLM_CUDA(c->n_jump.reserve(ld));
+    HLM_CUDA(c->tile_counter.reserve(1));
+    HLM_CUDA(c->totals.reserve(8));
+    HLM_CUDA(c->tq.reserve((size_t)std::max<long long>(nq, 1)));
+    if (nq > 0) HLM_CUDA(cudaMemcpyAsync(c->tq.p, tq, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, c->stream));
+    // y0 arrives [link][state]; stage it in the (not yet used) dense buffer, then transpose to columns
+    HLM_CUDA(c->dense[0].reserve((size_t)ns * m->n_eq));
+    HLM_CUDA(cudaMemcpyAsync(c->dense[0].p, y0, sizeof(double) * (size_t)ns * m->n_eq, cudaMemcpyHostToDevice, c->stream));
+    const hlm::SolverParams& prm = c->params[uid];
+    const int tpb = 256;
+    init_state_kernel<<<(unsigned)((c->ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+        c->dense[0].p, m->n_eq, ns, c->ld, c->y.p, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p,
+        c->n_acc.p, c->n_rej.p, c->n_jump.p, t0, prm.initialStep);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    int r = 0;
+    if (uid == hlm::Model204::UID) r = prepare_params<hlm::Model204>(c);
+    if (r) return r;
+    c->in_session = true;
+    return HLM_OK;
+}
+
+int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
+    HLM_REQUIRE(c, "hlm_solve_window: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_window: no session (call hlm_solve_begin)");
+    if (int r = use_device(c)) return r;
+    if (q_hi > c->nq) q_hi = c->nq;
+    HLM_REQUIRE(q_hi >= c->q_done, "hlm_solve_window: q_hi must not move backwards");
+    const long long q_lo = c->q_done;
+    const long long qw = q_hi - q_lo;
+    const bool dense = want_dense && qw > 0;
+    int buf = c->dense_cur;
+    if (dense) {
+        buf = c->dense_cur ^ 1;
+        if (c->copy_pending[buf]) {  // the D2H that last read this buffer must finish before it is overwritten
+            HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
+            c->copy_pending[buf] = false;
+        }
+        const size_t elems = (size_t)c->ns * (size_t)qw * (size_t)c->n_eq;
+        HLM_CUDA(c->dense[buf].reserve(elems));
+        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
+        c->dense_cur = buf;
+    }
+    hlm::WindowArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.y = c->y.p; a.t = c->t.p; a.h = c->h.p; a.next_q = c->next_q.p; a.reject_run = c->reject_run.p;
+    a.status = c->status.p; a.n_accept = c->n_acc.p; a.n_reject = c->n_rej.p; a.n_jump = c->n_jump.p;
+    a.sp = c->sp_soa.p;
+    a.col = c->forc_col_n ? c->forc_col.p : nullptr;
+    a.n_forc = c->n_forc;
+    for (int j = 0; j < 2; ++j) {
+        a.forc[j] = c->forc[j].p;
+        a.forc_nT[j] = c->forc_nT[j];
+        a.forc_dt_min[j] = c->forc_dt_h[j] * 60.0;  // rk45_kernel.cu:90
+    }
+    a.forc_ncols = c->forc_ncols;
+    a.tq = c->tq.p;
+    a.nq = (int)c->nq;
+    a.q_lo = (int)q_lo;
+    a.q_hi = (int)q_hi;
+    a.dense = dense ? c->dense[buf].p : nullptr;
+    a.t0 = c->t0; a.tf = c->tf;
+    a.prm = c->params[c->uid];
+    a.ns = c->ns; a.ld = c->ld;
+    a.max_attempts = c->max_attempts;
+    a.tile_counter = c->tile_counter.p;
+    if (int r = dispatch_window(c, a)) return r;
+    c->q_done = q_hi;
+    c->win_q_lo = q_lo;
+    c->win_q_hi = q_hi;
+    c->win_has_dense = dense;
+    if (dense) HLM_CUDA(cudaEventRecord(c->ev_kernel_done[buf], c->stream));
+    return HLM_OK;
+}
+
+int hlm_solve_window_buffer(hlm_ctx* c, void** dev_ptr, long long* q_lo, long long* q_hi) {
+    HLM_REQUIRE(c, "hlm_solve_window_buffer: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_window_buffer: no session");
+    if (dev_ptr) *dev_ptr = c->win_has_dense ? (void*)c->dense[c->dense_cur].p : nullptr;
+    if (q_lo) *q_lo = c->win_q_lo;
+    if (q_hi) *q_hi = c->win_q_hi;
+    return HLM_OK;
+}
+
+int hlm_solve_fetch_window(hlm_ctx* c, double* host_dense) {
+    HLM_REQUIRE(c && host_dense, "hlm_solve_fetch_window: NULL argument");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_fetch_window: no session");
+    if (!c->win_has_dense) return HLM_OK;
+    if (int r = use_device(c)) return r;
+    const int buf = c->dense_cur;
+    const long long qw = c->win_q_hi - c->win_q_lo;
+    const size_t row = (size_t)qw * c->n_eq * sizeof(double);         // one link's records of this window
+    const size_t host_pitch = (size_t)c->nq * c->n_eq * sizeof(double);  // one link's records of the run
+    HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
+    double* dst = host_dense + (size_t)c->win_q_lo * c->n_eq;
+    if (row == host_pitch)
+        HLM_CUDA(cudaMemcpyAsync(dst, c->dense[buf].p, row * (size_t)c->ns, cudaMemcpyDeviceToHost, c->copy_stream));
+    else
+        HLM_CUDA(cudaMemcpy2DAsync(dst, host_pitch, c->dense[buf].p, row, row, (size_t)c->ns, cudaMemcpyDeviceToHost,
+                                   c->copy_stream));
+    HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
+    c->copy_pending[buf] = true;
+    return HLM_OK;
+}
+
+int hlm_solve_totals(hlm_ctx* c, long long totals[7]) {
+    HLM_REQUIRE(c && totals, "hlm_solve_totals: NULL argument");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_totals: no session");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(cudaMemsetAsync(c->totals.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    const int tpb = 256;
+    const unsigned grid = (unsigned)std::min<long long>((c->ns + tpb - 1) / tpb, (long long)c->sm_count * 8);
+    totals_kernel<<<grid, tpb, 0, c->stream>>>(c->n_acc.p, c->n_rej.p, c->n_jump.p, c->status.p, c->ns, c->totals.p);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    unsigned long long h[8];
+    HLM_CUDA(cudaMemcpyAsync(h, c->totals.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 7; ++k) totals[k] = (long long)h[k];
+    return HLM_OK;
+}
+
+int hlm_solve_peek(hlm_ctx* c, double* out_t, double* out_h, double* out_y) {
+    HLM_REQUIRE(c, "hlm_solve_peek: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_peek: no session");
+    if (int r = use_device(c)) return r;
+    if (out_t) HLM_CUDA(cudaMemcpyAsync(out_t, c->t.p, sizeof(double) * (size_t)c->ns, cudaMemcpyDeviceToHost, c->stream));
+    if (out_h) HLM_CUDA(cudaMemcpyAsync(out_h, c->h.p, sizeof(double) * (size_t)c->ns, cudaMemcpyDeviceToHost, c->stream));
+    if (out_y)  // raw columns [N_EQ][ns]
+        HLM_CUDA(cudaMemcpy2DAsync(out_y, sizeof(double) * (size_t)c->ns, c->y.p, sizeof(double) * (size_t)c->ld,
+                                   sizeof(double) * (size_t)c->ns, (size_t)c->n_eq, cudaMemcpyDeviceToHost, c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    return HLM_OK;
+}
+
+int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_acc, long long* out_rej,
+                  long long* out_jump) {
+    HLM_REQUIRE(c, "hlm_solve_end: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_end: no session");
+    if (int r = use_device(c)) return r;
+    const long long ns = c->ns;
+    if (out_final) {
+        // the window buffer not used last is free to stage the transposed final states
+        const int buf = c->dense_cur ^ 1;
+        if (c->copy_pending[buf]) {
+            HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
+            c->copy_pending[buf] = false;
+        }
+        HLM_CUDA(c->dense[buf].reserve((size_t)ns * c->n_eq));
+        const int tpb = 256;
+        gather_final_kernel<<<(unsigned)((ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, c->status.p, c->n_eq, ns,
+                                                                                   c->ld, c->dense[buf].p);
+        HLM_CUDA(cudaGetLastError());
+        ++c->launches;
+        HLM_CUDA(cudaMemcpyAsync(out_final, c->dense[buf].p, sizeof(double) * (size_t)ns * c->n_eq,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    }
+    std::vector<unsigned int> tmp;
+    std::vector<int> st;
+    try {
+        if (out_acc || out_rej || out_jump) tmp.resize((size_t)ns);
+        if (out_stiff) st.resize((size_t)ns);
+    } catch (const std::bad_alloc&) {
+        return fail(HLM_ERR_NOMEM, "hlm_solve_end: out of host memory");
+    }
+    auto fetch = [&](const unsigned int* dev, long long* out) -> int {
+        if (!out) return 0;
+        HLM_CUDA(cudaMemcpyAsync(tmp.data(), dev, sizeof(unsigned int) * (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
+        HLM_CUDA(cudaStreamSynchronize(c->stream));
+        for (long long i = 0; i < ns; ++i) out[i] = (long long)tmp[(size_t)i];
+        return 0;
+    };
+    if (int r = fetch(c->n_acc.p, out_acc)) return r;
+    if (int r = fetch(c->n_rej.p, out_rej)) return r;
+    if (int r = fetch(c->n_jump.p, out_jump)) return r;
+    if (out_stiff) {
+        HLM_CUDA(cudaMemcpyAsync(st.data(), c->status.p, sizeof(int) * (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
+        HLM_CUDA(cudaStreamSynchronize(c->stream));
+        for (long long i = 0; i < ns; ++i) {
+            const int s = st[(size_t)i];
+            out_stiff[i] = (s == hlm::kStiff) ? HLM_LINK_STIFF : (s == hlm::kDone ? HLM_LINK_OK : HLM_LINK_STALLED);
+        }
+    }
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;
+    return HLM_OK;
+}
+
+int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
+                 long long nq, double* out_final, double* out_dense, int* out_stiff, long long* out_acc,
+                 long long* out_rej, long long* out_jump) {
+    if (!out_dense) nq = 0;  // nothing to emit: one window straight to tf
+    if (int r = hlm_solve_begin(c, uid, y0, ns, t0, tf, tq, nq)) return r;
+    if (nq == 0) {
+        if (int r = hlm_solve_window(c, 0, 0)) return r;
+    } else {
+        const long long per_q = ns * c->n_eq * (long long)sizeof(double);
+        long long qw = std::max<long long>(1, c->dense_window_bytes / per_q);
+        // the last window also runs to tf; keep windows even so the tail is not a sliver
+        const long long n_win = (nq + qw - 1) / qw;
+        qw = (nq + n_win - 1) / n_win;
+        for (long long q = 0; q < nq;) {
+            q = std::min(nq, q + qw);
+            if (int r = hlm_solve_window(c, q, 1)) return r;
+            if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
+        }
+    }
+    return hlm_solve_end(c, out_final, out_stiff, out_acc, out_rej, out_jump);
+}
+
+int hlm_measure_fma_peak(hlm_ctx* c, int bits, double* tflops) {
+    HLM_REQUIRE(c && tflops && (bits == 64 || bits == 32), "hlm_measure_fma_peak: bad argument");
+    if (int r = use_device(c)) return r;
+    const int tpb = 256, blocks = c->sm_count * 8, iters = 4096;
+    void* out = nullptr;
+    HLM_CUDA(cudaMalloc(&out, (size_t)tpb * blocks * 8));
+    cudaEvent_t e0, e1;
+    HLM_CUDA(cudaEventCreate(&e0));
+    HLM_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        HLM_CUDA(cudaEventRecord(e0, c->stream));
+        if (bits == 64) fma_peak_kernel<double><<<blocks, tpb, 0, c->stream>>>((double*)out, iters, 1.0);
+        else fma_peak_kernel<float><<<blocks, tpb, 0, c->stream>>>((float*)out, iters, 1.0f);
+        HLM_CUDA(cudaEventRecord(e1, c->stream));
+        HLM_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        HLM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+        c->launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    const double flops = 2.0 * 64.0 * (double)iters * tpb * blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return HLM_OK;
+}
+
+}  // extern "C"

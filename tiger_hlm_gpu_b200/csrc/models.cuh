@@ -1,0 +1,131 @@
+// models.cuh — device-side model definitions (the Model trait's `rhs`, compiled into the library).
+//
+// The reference's Model trait (models/model_204.hpp:15-115) hands `rhs` a pointer to the AoS
+// SpatialParams array and the link index and re-reads 15 doubles from it on every call.  A device
+// function cannot cross a C ABI, so models live here and are selected by UID at the boundary.
+// Each model declares
+//   UID, N_EQ          as in the reference trait
+//   N_SP               number of per-link SoA parameter columns it needs
+//   N_FORC             number of forcings its rhs reads (F[0] = rain, F[1] = temperature)
+//   prepare()          one AoS record -> its SoA columns (run once at upload)
+//   Link               the per-link constants held in registers for a whole window
+//   rhs()              the right-hand side, written with fp<T> primitives only
+#pragma once
+#include "fp_exact.cuh"
+
+namespace hlm {
+
+// Byte layout of the reference's SpatialParams (I_O/parameters_loader.hpp:19-37): 2 x i64 + 15 x f64.
+struct SpatialParamsAoS {
+    long long stream, next_stream;
+    double c1, infil, perco, Hu, lat, sw, ss, n_mann, slope, L, A_h, alpha3, alpha4, melt_f, temp_thr;
+};
+static_assert(sizeof(SpatialParamsAoS) == 136, "must match the reference's 136-byte record");
+
+// ---------------------------------------------------------------------------------------------
+// Model 204 — snow / static / surface / gravitational / aquifer storages.
+// Arithmetic follows models/model_204.hpp:54-113 operation by operation, with the two
+// contractions nvcc makes in the reference build (`d1 - s*Emax`, `d2 - h_surf*w`) written as fma.
+// Hoisted out of rhs because they depend on parameters only and are correctly rounded, hence
+// identical whenever computed: 1.0/n_mann (rcp.rn) and sqrt(slope) (sqrt.rn).
+// ---------------------------------------------------------------------------------------------
+struct Model204 {
+    static constexpr int UID = 204;
+    static constexpr int N_EQ = 5;
+    static constexpr int N_SP = 11;
+    static constexpr int N_FORC = 2;
+    enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR };
+
+    static __device__ __forceinline__ void prepare(const SpatialParamsAoS& s, double* out) {
+        out[INFIL] = s.infil;
+        out[PERCO] = s.perco;
+        out[HU] = s.Hu;
+        out[INV_N] = __drcp_rn(s.n_mann);
+        out[SQRT_SLOPE] = __dsqrt_rn(s.slope);
+        out[LEN] = s.L;
+        out[A_H] = s.A_h;
+        out[ALPHA3] = s.alpha3;
+        out[ALPHA4] = s.alpha4;
+        out[MELT_F] = s.melt_f;
+        out[TEMP_THR] = s.temp_thr;
+    }
+
+    template <typename T> struct Link {
+        T p[N_SP];
+        __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld, long long sys) {
+#pragma unroll
+            for (int i = 0; i < N_SP; ++i) p[i] = (T)__ldg(sp + (long long)i * ld + sys);
+        }
+    };
+
+    template <typename T>
+    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt) {
+        using f = fp<T>;
+        const T h_snow = y[0], h_stat = y[1], h_surf = y[2], h_grav = y[3], h_aq = y[4];
+        const T rainfall = F[0], temperature = F[1];
+
+        // 1) snow
+        const T snowmelt = (temperature >= P.p[TEMP_THR]) ? f::min(h_snow, f::mul(temperature, P.p[MELT_F])) : (T)0;
+        const T x1 = f::add(rainfall, snowmelt);
+        dydt[0] = f::sub(rainfall, snowmelt);
+
+        // 2) static
+        const T x2 = f::max((T)0, f::sub(f::add(x1, h_stat), P.p[HU]));
+        const T d1 = f::sub(x1, x2);
+        const T Emax = f::min(f::mul((T)0.1, temperature), h_stat);
+        const T s = f::div(h_stat, P.p[HU]);
+        dydt[1] = f::fma(-s, Emax, d1);
+
+        // 3) surface.  When h_surf is +-0 the reference's expression collapses exactly:
+        // pow(+-0, 2/3) = +0, so w is 0 (or 1 if L/A_h make a NaN, which fmin drops) and
+        // fma(-h_surf, w, d2) adds a signed zero to d2 >= +0, i.e. returns d2 bit for bit.
+        // Skipping pow/div there is a warp-divergent but exact shortcut.
+        const T x3 = f::min(x2, P.p[INFIL]);
+        const T d2 = f::sub(x2, x3);
+        if (h_surf == (T)0) {
+            dydt[2] = d2;
+        } else {
+            const T alfa2 = f::mul(f::mul(P.p[INV_N], f::pow(h_surf, (T)(2.0 / 3.0))), P.p[SQRT_SLOPE]);
+            const T w = f::min((T)1, f::mul(f::div(f::mul(alfa2, P.p[LEN]), P.p[A_H]), (T)60));
+            dydt[2] = f::fma(-h_surf, w, d2);
+        }
+
+        // 4) gravitational (interflow), 5) aquifer (baseflow)
+        const T x4 = f::min(x3, P.p[PERCO]);
+        const T d3 = f::sub(x3, x4);
+        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::div(h_grav, P.p[ALPHA3]) : (T)0);
+        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div(h_aq, P.p[ALPHA4]) : (T)0);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// DummyModel — the 5-state linear test system of model_dummy_python.ipynb:65-89 (code cell,
+// I2 = 0.6*H1).  The reference ships no C++ for it; operations are unfused, in the
+// order Python evaluates the notebook's expressions, and match oracle/oracle_rk45.c:rhs_dummy.
+// UID 0 is this project's choice (the reference never assigned one).
+// ---------------------------------------------------------------------------------------------
+struct DummyModel {
+    static constexpr int UID = 0;
+    static constexpr int N_EQ = 5;
+    static constexpr int N_SP = 0;
+    static constexpr int N_FORC = 0;
+    static __device__ __forceinline__ void prepare(const SpatialParamsAoS&, double*) {}
+    template <typename T> struct Link {
+        __device__ __forceinline__ void load(const double*, long long, long long) {}
+    };
+    template <typename T>
+    static __device__ __forceinline__ void rhs(const T* y, const T*, const Link<T>&, T* dydt) {
+        using f = fp<T>;
+        const T Y0 = f::mul((T)0.5, y[0]);
+        const T X2 = f::mul((T)0.3, y[1]);
+        const T I2 = f::mul((T)0.6, y[1]);
+        const T I3 = f::mul((T)0.4, y[3]);
+        dydt[0] = f::sub((T)1.0, Y0);
+        dydt[1] = f::sub(f::sub(f::sub(f::add((T)1.2, Y0), X2), (T)0.4), I2);
+        dydt[2] = f::sub(X2, (T)0.2);
+        dydt[3] = f::sub(f::sub(I2, I3), (T)0.3);
+        dydt[4] = f::sub(I3, (T)0.1);
+    }
+};
+
+}  // namespace hlm

@@ -1,0 +1,338 @@
+// rk45_window.cuh — the hot path: batched adaptive Dormand–Prince 5(4) over one output window.
+//
+// Replaces the reference kernel rk45_then_radau_multi<Model> (solver/rk45_kernel.cu:17-176) and the
+// device functions it inlines: rk45_step (solver/rk45_step_dense.cuh:33-145), rk45_dense
+// (solver/rk45_step_dense.cuh:171-244) and norm_inf_diff (solver/event_detector.cuh:46-53).
+//
+// Same per-link algorithm, same FP operations in the same order (see fp_exact.cuh), different
+// machine mapping:
+//   * one lane per link, one warp per tile of 32 consecutive links, persistent warps that pull
+//     tiles from an atomic counter — no __syncthreads anywhere, grid = SMs x resident CTAs;
+//   * state, per-link parameters and counters are structure-of-arrays: every load/store of a tile
+//     is one coalesced 256-byte line per column;
+//   * all seven stage slopes, the state and the link parameters stay in registers for the whole
+//     window (the reference keeps k[7][5] and its forcing slice on a 352-byte local stack and
+//     re-reads 15 AoS doubles per rhs call);
+//   * forcings stay on their GRID ([time][cell], shared by ~500 links per cell) and are re-read
+//     only when a lane's time leaves the validity interval of its current sample; the exact
+//     IEEE index computation of the reference runs only then;
+//   * k0 is re-used whenever that is bit-safe: after a rejected or slope-jump attempt (t, y, F
+//     unchanged) and, FSAL, after an accepted step whose stage-6 state equals y_next bit for bit
+//     with the forcing sample unchanged;
+//   * the run is cut into query windows so the dense output of a window fits in HBM; a lane that
+//     has emitted every query of the window pauses with its complete loop state saved, which is
+//     invisible to the step sequence (no clipping of h at window edges);
+//   * dense records are written as contiguous 40-byte rows of the final [link][query][state]
+//     layout the reference's host reorder (solver/rk45_api.hpp:255-267) produces, so there is no
+//     reorder pass on either side.
+#pragma once
+#include "fp_exact.cuh"
+#include "models.cuh"
+
+namespace hlm {
+
+// Dormand–Prince tableau, same expressions as solver/rk45_step_dense.cuh:54-83 so the constants
+// round identically.  Zero entries are kept: the reference multiplies through them and with a
+// non-finite slope that matters (0*inf = NaN).
+namespace dp {
+__device__ constexpr double A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5.0, 0, 0, 0, 0, 0},
+    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
+    {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
+__device__ constexpr double B[7] = {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0,
+                                    -2187.0 / 6784.0, 11.0 / 84.0, 0.0};
+__device__ constexpr double BALT[7] = {5179.0 / 57600.0, 0.0, 7571.0 / 16695.0, 393.0 / 640.0,
+                                       -92097.0 / 339200.0, 187.0 / 2100.0, 1.0 / 40.0};
+// solver/rk45_step_dense.cuh:193-219
+__device__ constexpr double P[7][4] = {
+    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
+    {0.0, 0.0, 0.0, 0.0},
+    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
+    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
+    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
+    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
+    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+}  // namespace dp
+
+// solver/event_detector.cuh:11,15
+constexpr double kSlopeJumpThresh = 100.0;
+constexpr double kMinStepFraction = 1e-6;
+
+enum LinkStatus : int { kActive = 0, kDone = 1, kStiff = 2, kStalled = 3 };
+
+constexpr int kMaxForcings = 16;  // I_O/forcing_data.h:5
+
+struct SolverParams {  // Model::Parameters, models/model_204.hpp:22-30
+    double initialStep, rtol, atol, safety, minScale, maxScale;
+};
+
+// Everything one window launch needs.  Passed by value (fits the 4 KB parameter space).
+struct WindowArgs {
+    // resident per-link state, SoA, leading dimension ld (ns rounded up to 32)
+    double* y;             // [N_EQ][ld]
+    double* t;             // [ld]
+    double* h;             // [ld]
+    int* next_q;           // [ld]
+    int* reject_run;       // [ld]   consecutive rejections (rk45_kernel.cu:130,155)
+    int* status;           // [ld]   LinkStatus
+    unsigned int* n_accept;  // [ld]
+    unsigned int* n_reject;  // [ld]
+    unsigned int* n_jump;    // [ld]
+    const double* sp;      // [N_SP][ld]  model-prepared parameter columns
+    const int* col;        // [ld] forcing column (grid cell) per link, or nullptr = link index
+    const float* forc[2];  // forcing j: [nT][ncols]
+    long long forc_nT[2];
+    double forc_dt_min[2];  // c_forc_dt[j] * 60.0, rk45_kernel.cu:90
+    long long forc_ncols;
+    int n_forc;            // forcings present (0..2 used by the models here)
+    const double* tq;      // [nq] ascending
+    int nq;
+    int q_lo, q_hi;        // this window's dense buffer covers queries [q_lo, q_hi)
+    double* dense;         // [ns][q_hi - q_lo][N_EQ] or nullptr
+    double t0, tf;
+    SolverParams prm;
+    long long ns, ld;
+    long long max_attempts;  // per link per launch; <=0 = unbounded like the reference
+    unsigned int* tile_counter;
+};
+
+template <typename T, int N>
+struct StepOut {
+    T err;
+};
+
+// One DOPRI5 attempt from (y, k0): fills k[1..6], y6 (stage-6 state), y_next, returns err.
+// solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
+template <class Model, typename T>
+__device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][Model::N_EQ], T h,
+                                           const T* F, const typename Model::template Link<T>& L, T rtol, T atol,
+                                           T (&y6)[Model::N_EQ], T (&y_next)[Model::N_EQ]) {
+    using f = fp<T>;
+    constexpr int N = Model::N_EQ;
+#pragma unroll
+    for (int s = 1; s < 7; ++s) {
+        T ha[6];
+#pragma unroll
+        for (int j = 0; j < s; ++j) ha[j] = f::mul(h, (T)dp::A[s][j]);
+        T yt[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T acc = y[i];
+#pragma unroll
+            for (int j = 0; j < s; ++j) acc = f::fma(ha[j], k[j][i], acc);
+            yt[i] = acc;
+        }
+        Model::template rhs<T>(yt, F, L, k[s]);
+        if (s == 6) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) y6[i] = yt[i];
+        }
+    }
+    // y_out = y + sum_{s<7} (h*b[s])*k[s].  a[6][j] == b[j] bit for bit for j < 6, so the first six
+    // terms ARE y6; only the last (zero-weight) term remains.
+    {
+        const T hb6 = f::mul(h, (T)dp::B[6]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y_next[i] = f::fma(hb6, k[6][i], y6[i]);
+    }
+    T he[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) he[s] = f::mul(h, (T)(dp::B[s] - dp::BALT[s]));
+    T max_ratio = (T)0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T e = (T)0;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) e = f::fma(he[s], k[s][i], e);
+        const T ymax = f::max(f::abs(y[i]), f::abs(y_next[i]));
+        const T tol = f::fma(rtol, ymax, atol);
+        const T ratio = f::abs(f::div(e, tol));
+        if (ratio > max_ratio) max_ratio = ratio;  // NaN-ignoring form of the reference
+    }
+    return max_ratio;
+}
+
+// Exact forcing sample index of the reference (rk45_kernel.cu:90-98) plus a conservative interval
+// [lo, hi) of times for which that index is certain to be the same: 1e-9 relative inside the
+// sample's edges, far beyond the rounding of t/dt_min.  Outside it the caller recomputes exactly.
+__device__ __forceinline__ long long forcing_index(double t, double dt_min, long long nT, double& lo, double& hi) {
+    const double r = __ddiv_rn(t, dt_min);
+    long long idx = (r < 0.0) ? 0 : ((r >= (double)nT) ? nT - 1 : (long long)r);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    lo = (idx <= 0) ? -inf : (double)idx * dt_min * (1.0 + 1e-9);
+    hi = (idx >= nT - 1) ? inf : (double)(idx + 1) * dt_min * (1.0 - 1e-9);
+    if (!(dt_min > 0.0)) { lo = inf; hi = -inf; }  // degenerate spacing: never cache
+    return idx;
+}
+
+template <class Model, typename T>
+__global__ void __launch_bounds__(128, 3) rk45_window_kernel(const WindowArgs a) {
+    using f = fp<T>;
+    constexpr int N = Model::N_EQ;
+    const int lane = threadIdx.x & 31;
+    const long long n_tiles = (a.ns + 31) >> 5;
+    const bool run_to_end = (a.q_hi >= a.nq);
+    const int qw = a.q_hi - a.q_lo;
+    const T rtol = (T)a.prm.rtol, atol = (T)a.prm.atol;
+    const T safety = (T)a.prm.safety, minScale = (T)a.prm.minScale, maxScale = (T)a.prm.maxScale;
+    const T h_floor = f::mul((T)a.prm.initialStep, (T)kMinStepFraction);     // rk45_kernel.cu:134
+    const T h_stiff = f::mul(f::sub((T)a.tf, (T)a.t0), (T)kMinStepFraction);  // rk45_kernel.cu:160
+    const T tf = (T)a.tf;
+
+    for (;;) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if ((long long)tile >= n_tiles) break;
+        const long long sys = ((long long)tile << 5) + lane;
+        if (sys >= a.ns) continue;
+        int status = a.status[sys];
+        if (status != kActive) continue;
+
+        // ---- load lane state (coalesced columns) ----
+        T y[N], k[7][N], y6[N], y_next[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = (T)a.y[(long long)i * a.ld + sys];
+        T t = (T)a.t[sys], h = (T)a.h[sys];
+        int next_q = a.next_q[sys];
+        int reject_run = a.reject_run[sys];
+        unsigned int n_acc = a.n_accept[sys], n_rej = a.n_reject[sys], n_jmp = a.n_jump[sys];
+        typename Model::template Link<T> L;
+        L.load(a.sp, a.ld, sys);
+        const long long col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
+
+        T F[2] = {(T)0, (T)0};
+        double f_lo = fp<double>::inf(), f_hi = -fp<double>::inf();  // empty validity interval
+        T tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
+        bool k0_valid = false;
+        long long budget = a.max_attempts;
+
+        for (;;) {
+            if (!(t < tf)) { status = kDone; break; }
+            if (!run_to_end && next_q >= a.q_hi) break;  // window complete for this link: pause
+            if (a.max_attempts > 0 && budget-- <= 0) { status = kStalled; break; }
+            if (f::add(t, h) > tf) h = f::sub(tf, t);  // rk45_kernel.cu:54
+
+            // ---- forcing sample at the step-start time, held for all stages ----
+            if (Model::N_FORC > 0 && a.n_forc > 0) {
+                const double td = (double)t;
+                if (!(td >= f_lo && td < f_hi)) {
+                    f_lo = -fp<double>::inf();
+                    f_hi = fp<double>::inf();
+#pragma unroll
+                    for (int j = 0; j < Model::N_FORC; ++j) {
+                        if (j < a.n_forc) {
+                            double lo, hi;
+                            const long long idx = forcing_index(td, a.forc_dt_min[j], a.forc_nT[j], lo, hi);
+                            const T v = (T)__ldg(a.forc[j] + idx * a.forc_ncols + col);  // f32 -> f64 widening as model_204.hpp:82-83
+                            if (!f::same_bits(v, F[j])) k0_valid = false;
+                            F[j] = v;
+                            f_lo = fmax(f_lo, lo);
+                            f_hi = fmin(f_hi, hi);
+                        }
+                    }
+                }
+            }
+
+            if (!k0_valid) Model::template rhs<T>(y, F, L, k[0]);  // rk45_kernel.cu:114
+            const T err = dopri_attempt<Model, T>(y, k, h, F, L, rtol, atol, y6, y_next);
+
+            if (err <= (T)1) {
+                reject_run = 0;
+                // slope-jump detection, event_detector.cuh:46-53 + rk45_kernel.cu:132-136
+                T jump = (T)0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const T d = f::abs(f::sub(k[0][i], k[1][i]));
+                    if (d > jump) jump = d;
+                }
+                if (jump > (T)kSlopeJumpThresh) {
+                    h = f::max(f::mul(h, (T)0.5), h_floor);
+                    ++n_jmp;
+                    k0_valid = true;  // same t, y, F
+                    continue;
+                }
+                const T t1 = f::add(t, h);
+                // ---- dense output for queries in (t, t1], rk45_kernel.cu:139-148 ----
+                bool overshoot = false;
+                if (next_q < a.nq && tq_next <= t1) {
+                    // Q depends on the step only: built once here, not per query as the reference does.
+                    T Q[4][N];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            T sum = (T)0;
+#pragma unroll
+                            for (int j = 0; j < 7; ++j) sum = f::fma((T)dp::P[j][m], k[j][i], sum);
+                            Q[m][i] = sum;
+                        }
+                    do {
+                        if (next_q >= a.q_hi) { overshoot = true; break; }
+                        if (tq_next > t && a.dense != nullptr) {
+                            const T th = f::div(f::sub(tq_next, t), h);
+                            double* out = a.dense + ((long long)sys * qw + (next_q - a.q_lo)) * N;
+                            const T th2 = f::mul(th, th), th3 = f::mul(th2, th), th4 = f::mul(th3, th);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                T poly = f::fma(Q[0][i], th, (T)0);
+                                poly = f::fma(Q[1][i], th2, poly);
+                                poly = f::fma(Q[2][i], th3, poly);
+                                poly = f::fma(Q[3][i], th4, poly);
+                                out[i] = (double)f::fma(h, poly, y[i]);
+                            }
+                        }
+                        ++next_q;
+                        tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
+                    } while (next_q < a.nq && tq_next <= t1);
+                }
+                if (overshoot) break;  // step spans past this window's buffer: leave it uncommitted, redo next window
+
+                // FSAL: k6 = rhs(y6, F).  It is the next k0 iff y_next == y6 bit for bit (the zero-weight
+                // b[6] term changed nothing) and the forcing sample is unchanged (checked next iteration).
+                bool fsal = true;
+#pragma unroll
+                for (int i = 0; i < N; ++i) fsal = fsal && f::same_bits(y_next[i], y6[i]);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    y[i] = y_next[i];
+                    k[0][i] = k[6][i];
+                }
+                k0_valid = fsal;
+                t = t1;
+                ++n_acc;
+                const T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
+                h = f::mul(h, f::min(f::max(fac, minScale), maxScale));
+            } else {
+                ++reject_run;
+                ++n_rej;
+                T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
+                fac = f::min(fac, (T)1);
+                fac = f::min(f::max(fac, minScale), maxScale);
+                h = f::mul(h, fac);
+                k0_valid = true;  // same t, y, F
+                if (reject_run > 5 || h < h_stiff) { status = kStiff; break; }  // rk45_kernel.cu:160-162
+            }
+        }
+        // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
+        // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
+
+        // ---- store lane state ----
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.y[(long long)i * a.ld + sys] = (double)y[i];
+        a.t[sys] = (double)t;
+        a.h[sys] = (double)h;
+        a.next_q[sys] = next_q;
+        a.reject_run[sys] = reject_run;
+        a.status[sys] = status;
+        a.n_accept[sys] = n_acc;
+        a.n_reject[sys] = n_rej;
+        a.n_jump[sys] = n_jmp;
+    }
+}
+
+}  // namespace hlm
