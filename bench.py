@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — accepted RK45 system-steps/s of the batched Dormand–Prince path on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (for N > 1 launched under torchrun, one
+rank per GPU).  One JSON line on rank 0.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): Model204, synthetic
+links (SURVEY §8(d) inputs), 1-year hourly precipitation + daily temperature on a forcing grid,
+hourly dense output, FP64.  A *step* is one output window = one simulated day for every link of the
+rank (24 hourly queries, ~450 accepted RK45 steps per link).  Links are sharded over ranks with no
+data-path collective (they are independent); scaling is weak: --links-per-gpu links
+on every rank.
+
+  value  accepted system-steps/s with state, parameters and forcings resident in HBM and the dense
+         window left on the device (hlm_solve_window), CUDA events on the launching stream,
+         max over ranks.
+  e2e    the same metric through the reference-facing operator hlm_run_rk45 (the C ABI under
+         rk45_api::run_rk45<T>) with HOST buffers: every step uploads y0 from pinned memory and
+         downloads final + dense states.
+  roofline / cpu_baseline / reference_cuda / clocks: see DESIGN.md §Measurement.
+
+`--impl reference` times the reference's own CPU implementation of the path instead: its
+rk45_step / rk45_dense / Model204::rhs templates compiled for the host from the reference sources
+(oracle/_ref/libref_host.so) on all host cores, each step a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_MIN_FLOP_PER_ATTEMPT = 561.0  # minimal-algorithm nominal FP64 flop per attempted Model204 step
+PRM6 = [1e-6, 1e-6, 1e-9, 0.9, 0.2, 10.0]  # initialStep (main.cpp:633-640), rtol, atol, safety, min/maxScale
+DAY = 1440.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--links-per-gpu", type=int, default=10_000_000)
+    ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
+    ap.add_argument("--wet-fraction", type=float, default=0.0,
+                    help="share of links started with surface storage so Model204's pow() branch runs")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference_cuda legs")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(ns: int, days: int, wet_fraction: float, rank: int):
+    from tiger_hlm_gpu_b200 import synthetic
+    sp = synthetic.make_spatial_params(ns, seed=204 + rank)
+    col, ncells = synthetic.make_cells(ns)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days, seed=2019 + rank)
+    y0 = synthetic.make_y0(ns, wet_fraction, seed=7 + rank)
+    return sp, col, ncells, pr, t2m, y0
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_inputs(ns_sample: int, args):
+    """A bounded sample of the SAME workload: the first ns_sample links of rank 0's shard, day 0."""
+    from tiger_hlm_gpu_b200 import synthetic
+    sp = synthetic.make_spatial_params(ns_sample, seed=204)
+    col, ncells = synthetic.make_cells(ns_sample)
+    pr, t2m = synthetic.make_forcing_grid(ncells, 2, seed=2019)
+    y0 = synthetic.make_y0(ns_sample, args.wet_fraction, seed=7)
+    tq = synthetic.hourly_queries(0.0, DAY)
+    return sp, col, pr, t2m, y0, tq
+
+
+def time_cpu(kind: str, ns_sample: int, threads: int, args):
+    """Accepted steps/s of the CPU path on `threads` host threads over ns_sample links x 1 day."""
+    from tiger_hlm_gpu_b200 import synthetic
+    sp, col, pr, t2m, y0, tq = cpu_sample_inputs(ns_sample, args)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        from tests import refs
+        blocks = [synthetic.expand_forcing_per_link(pr, col), synthetic.expand_forcing_per_link(t2m, col)]
+        r = refs.ref_host_run204(PRM6, y0, 0.0, DAY, tq, sp, blocks, [1.0, 24.0], threads=threads)
+    else:
+        from oracle import oracle as O
+        r = O.run_rk45(204, O.Params.make(*PRM6), y0, 0.0, DAY, tq, sp=sp,
+                       forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col), threads=threads)
+    dt = time.perf_counter() - t0
+    return float(r["n_accept"].sum()), dt
+
+
+def cpu_baseline(kind: str, args, target_s: float):
+    cores = os.cpu_count() or 1
+    pilot_ns = 64 * cores
+    acc, dt = time_cpu(kind, pilot_ns, cores, args)
+    rate = acc / dt
+    ns_sample = int(min(max(pilot_ns, target_s * rate / max(acc / pilot_ns, 1.0)), 4_000_000))
+    acc, dt = time_cpu(kind, ns_sample, cores, args)
+    return {"value": acc / dt, "unit": "accepted system-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{ns_sample} links x 1 simulated day (day 0 of the bench workload, hourly dense output), "
+                      f"{int(acc)} accepted steps in {dt:.2f} s wall on {cores} threads",
+            "ns_sample": ns_sample, "seconds": dt}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own step/dense/rhs code on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests import refs
+    kind = "reference" if refs.have("libref_host.so") else "port"
+    cores = os.cpu_count() or 1
+    # size one step for ~4 s so that warmup+steps end within a few minutes
+    acc, dt = time_cpu(kind, 64 * cores, cores, args)
+    per_link = acc / (64 * cores)
+    ns_sample = int(max(64 * cores, 4.0 * (acc / dt) / per_link))
+    for _ in range(args.warmup):
+        time_cpu(kind, ns_sample, cores, args)
+    tot_acc, tot_dt = 0.0, 0.0
+    for _ in range(args.steps):
+        a, d = time_cpu(kind, ns_sample, cores, args)
+        tot_acc += a
+        tot_dt += d
+    value = tot_acc / tot_dt
+    sample = (f"{ns_sample} links x 1 simulated day per step (first links of the bench workload, hourly dense "
+              f"output), {cores} host threads; step/dense/rhs are the reference's own templates compiled for the "
+              f"host, the driver loop restates solver/rk45_kernel.cu:53-164")
+    line = {
+        "impl": "reference", "metric": "accepted RK45 system-steps/sec", "value": value,
+        "unit": "accepted system-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, ns_sample),
+        "cpu_baseline": {"value": value, "unit": "accepted system-steps/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "accepted system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, ns):
+    return {"workload": "Model204 hillslope-link runoff, synthetic links (SURVEY 8(d) inputs), 1-year hourly "
+                        "pr + daily t2m forcing grid, hourly dense output; one step = one simulated day "
+                        "(24 queries) for every link",
+            "links_per_gpu": ns, "days_of_forcing": args.days, "queries_per_step": 24,
+            "wet_fraction": args.wet_fraction, "rtol": PRM6[1], "atol": PRM6[2], "initial_step": PRM6[0],
+            "parallelism": f"links sharded over {args.gpus} GPU(s), no collective",
+            "l2": "inputs larger than L2 (per-step state+parameter+output traffic >> 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import tiger_hlm_gpu_b200 as hlm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ns = args.links_per_gpu
+    K, W = args.steps, args.warmup
+    assert W + K <= args.days, "not enough forcing days for warmup+steps"
+
+    sp, col, ncells, pr, t2m, y0 = make_inputs(ns, args.days, args.wet_fraction, rank)
+    solver = hlm.Solver(local_rank)
+    stream = torch.cuda.current_stream()
+    solver.set_stream(stream.cuda_stream)
+    solver.set_precision(args.precision)
+    solver.set_model_parameters(204, hlm.Parameters(*PRM6))
+    solver.set_max_attempts(5_000_000)
+    solver.upload_spatial_params(sp)
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(col)
+    fp_peak = solver.measure_fma_peak(args.precision)
+
+    # ---------------- resident arm: `value` ----------------
+    # One step = one simulated day: hlm_solve_restart (new interval from the resident final state,
+    # what a chained run_rk45 does) + hlm_solve_window (the hot kernel).  The run is driven in
+    # day-sized intervals because the reference's stiffness threshold scales with (tf - t0).
+    def day_queries(k):
+        return k * DAY + 60.0 * np.arange(1, 25)
+
+    solver.solve_begin(204, y0, 0.0, DAY, day_queries(0))
+    for k in range(W):
+        if k:
+            solver.solve_restart(k * DAY, (k + 1) * DAY, day_queries(k))
+        solver.solve_window(24, True)
+    solver.synchronize()
+    tot0 = solver.solve_totals()
+    solver.kernel_time_ms()  # drop warm-up kernel timings
+    launches0 = solver.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(W, W + K):
+        if k:
+            solver.solve_restart(k * DAY, (k + 1) * DAY, day_queries(k))
+        solver.solve_window(24, True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = solver.kernel_time_ms()
+    launches = solver.launch_count() - launches0
+    tot1 = solver.solve_totals()
+    acc = tot1["n_accept"] - tot0["n_accept"]
+    attempts = acc + (tot1["n_reject"] - tot0["n_reject"]) + (tot1["n_jump"] - tot0["n_jump"])
+    state = dict(tot1)
+    solver.solve_end()
+
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([acc, attempts, launches, kern_ms, kern_n], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_max = float(t_ms.item())
+    acc_all, att_all, launches_all, kern_ms_all, kern_n_all = [float(x) for x in sums.tolist()]
+    value = acc_all / (ms_max * 1e-3)
+
+    # ---------------- end-to-end arm: `e2e` ----------------
+    e2e = None
+    if not args.no_e2e:
+        nq_w = 24
+        y_host = torch.from_numpy(y0.copy()).pin_memory()
+        f_host = torch.zeros((ns, 5), dtype=torch.float64).pin_memory()
+        d_host = torch.zeros((ns, nq_w, 5), dtype=torch.float64).pin_memory()
+        stiff = np.zeros(ns, np.int32)
+        na = np.zeros(ns, np.int64)
+        lib = hlm.load_library()
+        import ctypes as C
+
+        def one_step(k):
+            t0 = k * DAY
+            tqw = t0 + 60.0 * np.arange(1, nq_w + 1)
+            rc = lib.hlm_run_rk45(solver._h, 204, C.c_void_p(y_host.data_ptr()), ns, t0, t0 + DAY,
+                                  tqw.ctypes.data_as(C.c_void_p), nq_w, C.c_void_p(f_host.data_ptr()),
+                                  C.c_void_p(d_host.data_ptr()), stiff.ctypes.data_as(C.c_void_p),
+                                  na.ctypes.data_as(C.c_void_p), None, None)
+            if rc != 0:
+                raise hlm.HlmError(lib.hlm_last_error().decode())
+            y_host.copy_(f_host)  # next day's initial state = this day's final state (host round trip)
+            return int(na.sum())
+
+        for k in range(W):
+            one_step(k)
+        barrier()
+        t_start = time.perf_counter()
+        ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ee0.record(stream)
+        acc_e = 0
+        for k in range(W, W + K):
+            acc_e += one_step(k)
+        ee1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t_start) * 1e3
+        # the call is synchronous at its end (results are in host memory), so wall clock and the event
+        # pair bracket the same work; report the larger
+        e_ms = max(ee0.elapsed_time(ee1), wall_ms)
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        se = torch.tensor([float(acc_e)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        h2d = ns * 5 * 8 + nq_w * 8
+        d2h = ns * 5 * 8 + ns * nq_w * 5 * 8 + ns * 4 + ns * 4
+        e2e = {"value": float(se.item()) / (float(te.item()) * 1e-3), "unit": "accepted system-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / K,
+               "api": "hlm_run_rk45 (C ABI under rk45_api::run_rk45<Model204>), pinned host buffers"}
+
+    # ---------------- baselines (rank 0, N == 1 only) ----------------
+    cpu = None
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_baselines:
+        try:
+            cpu = cpu_baseline("port", args, args.cpu_seconds)
+        except Exception as ex:  # the oracle library always exists; report rather than hide a failure
+            cpu = {"error": repr(ex)}
+        try:
+            from tests import refs
+            from tiger_hlm_gpu_b200 import synthetic
+            if refs.have("libref_cuda.so"):
+                ns_r = min(ns, 1 << 20)
+                blocks = [synthetic.expand_forcing_per_link(pr[:48], col[:ns_r]),
+                          synthetic.expand_forcing_per_link(t2m[:2], col[:ns_r])]
+                tq_r = 60.0 * np.arange(0, 25)
+                refs.ref_cuda_run204(PRM6, y0[:ns_r], 0.0, DAY, tq_r, sp[:ns_r], blocks, [1.0, 24.0], counted=False)
+                r = refs.ref_cuda_run204(PRM6, y0[:ns_r], 0.0, DAY, tq_r, sp[:ns_r], blocks, [1.0, 24.0], counted=True)
+                p = refs.ref_cuda_run204(PRM6, y0[:ns_r], 0.0, DAY, tq_r, sp[:ns_r], blocks, [1.0, 24.0], counted=False)
+                ref_cuda = {"value": float(r["n_accept"].sum()) / (p["kernel_ms"] * 1e-3),
+                            "unit": "accepted system-steps/s", "kernel_ms": p["kernel_ms"],
+                            "sample": f"unchanged reference kernel rk45_then_radau_multi<Model204> built for sm_100a, "
+                                      f"{ns_r} links x day 0 of the bench workload, 25 hourly queries, 1-D launch "
+                                      f"<<<ceil(ns/128),128>>>, per-link expanded forcing; kernel time only"}
+        except Exception as ex:
+            ref_cuda = {"error": repr(ex)}
+
+    if rank == 0:
+        hbm_peak, hbm_src = peaks()
+        kern_avg_ms = kern_ms_all / max(kern_n_all, 1)
+        att_per_launch = att_all / max(kern_n_all, 1)
+        achieved_tflops = W_MIN_FLOP_PER_ATTEMPT * att_per_launch / (kern_avg_ms * 1e-3) / 1e12
+        # algorithmic HBM bytes per link per window: state in+out, prepared parameters, forcing column,
+        # dense records, counters
+        bytes_per_link = (5 + 2) * 8 * 2 + 6 * 4 * 2 + 11 * 8 + 4 + 24 * 5 * 8
+        hbm_gbs = bytes_per_link * ns / (kern_avg_ms * 1e-3) / 1e9
+        line = {
+            "metric": "accepted RK45 system-steps/sec", "value": value, "unit": "accepted system-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
+            "data": "synthetic", "config": workload_config(args, ns),
+            "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),
+            "link_status_after_run": {k: state[k] for k in ("active", "done", "stiff", "stalled")},
+            "e2e": e2e, "gpu_launches": int(launches_all),
+            "roofline": {"bound": "fp64" if args.precision == 64 else "fp32",
+                         "achieved": achieved_tflops, "peak": fp_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / fp_peak, "traffic": None,
+                         "peak_source": "measured live: register-resident FMA microbenchmark (hlm_measure_fma_peak); "
+                                        "MEASURED_PEAKS.json holds no FP64/FP32 vector peak",
+                         "flop_per_attempt": W_MIN_FLOP_PER_ATTEMPT, "attempts_per_launch": att_per_launch,
+                         "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_window_kernel<Model204,double>",
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                                 "peak_source": hbm_src, "algorithmic_bytes_per_link_per_launch": bytes_per_link}},
+            "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

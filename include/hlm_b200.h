@@ -133,6 +133,13 @@ int hlm_run_rk45(hlm_ctx* ctx, int uid, const double* y0, long long ns, double t
 /* Upload y0 and the query times, reset per-link state (t = t0, h = initialStep, counters 0). */
 int hlm_solve_begin(hlm_ctx* ctx, int uid, const double* y0, long long ns, double t0, double tf,
                     const double* tq, long long nq);
+/* Start a new interval [t0, tf] from the resident final states: exactly what a second
+ * run_rk45(h_y0 = previous final, t0, tf, tq) does (t = t0, h = initialStep, query cursor 0; links
+ * flagged stiff/stalled stay flagged; counters keep accumulating) without moving states through
+ * the host.  This is how a long run is driven in forcing-sized chunks: the reference's stiffness
+ * threshold h < (tf - t0) * 1e-6 (solver/rk45_kernel.cu:160) scales with the interval, so a
+ * one-year interval would flag nearly every link, SURVEY §7.3. */
+int hlm_solve_restart(hlm_ctx* ctx, double t0, double tf, const double* tq, long long nq);
 /* Advance every unfinished link until it has emitted all queries with index < q_hi (to tf when
  * q_hi >= nq).  Dense records of queries [previous q_hi, q_hi) go to a device buffer
  * [ns][q_hi - q_lo][N_EQ] owned by the context (skipped when want_dense == 0).  Asynchronous. */
@@ -162,6 +169,11 @@ int hlm_kernel_time_ms(hlm_ctx* ctx, double* sum_ms, long long* n_launches);
  * TFLOP/s (2 flops per FMA).  Used as the roofline denominator, which MEASURED_PEAKS.json lacks
  * for FP64/FP32. bits = 64 or 32. */
 int hlm_measure_fma_peak(hlm_ctx* ctx, int bits, double* tflops);
+
+/* Element-wise probe of the device's arithmetic on host arrays x, y -> out (n elements):
+ * op 0 = libdevice pow(x, y); 1 = rcp.approx.ftz.f64(x) (the MUFU.RCP64H seed pow starts from);
+ * 2 = x / y (div.rn.f64); 3 = sqrt.rn.f64(x).  Lets tests compare device and host arithmetic. */
+int hlm_debug_eval(hlm_ctx* ctx, int op, const double* x, const double* y, double* out, long long n);
 
 #ifdef __cplusplus
 }

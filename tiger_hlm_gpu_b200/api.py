@@ -51,6 +51,7 @@ SIGNATURES = {
     "hlm_set_precision": (_I, [_V, _I]),
     "hlm_run_rk45": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL, _V, _V, _V, _V, _V, _V]),
     "hlm_solve_begin": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL]),
+    "hlm_solve_restart": (_I, [_V, _D, _D, _V, _LL]),
     "hlm_solve_window": (_I, [_V, _LL, _I]),
     "hlm_solve_window_buffer": (_I, [_V, C.POINTER(_V), C.POINTER(_LL), C.POINTER(_LL)]),
     "hlm_solve_fetch_window": (_I, [_V, _V]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "hlm_launch_count": (_LL, [_V]),
     "hlm_kernel_time_ms": (_I, [_V, C.POINTER(_D), C.POINTER(_LL)]),
     "hlm_measure_fma_peak": (_I, [_V, _I, C.POINTER(_D)]),
+    "hlm_debug_eval": (_I, [_V, _I, _V, _V, _V, _LL]),
 }
 
 
@@ -233,6 +235,13 @@ class Solver:
         _check(self._lib.hlm_solve_begin(self._h, uid, _p(y0), y0.shape[0], t0, tf, _p(tq), tq.shape[0]))
         self._keep += [y0, tq]
 
+    def solve_restart(self, t0: float, tf: float, tq):
+        tq = np.ascontiguousarray(tq if tq is not None else [], dtype=np.float64)
+        uid, n_eq, ns, _ = self._session
+        self._session = (uid, n_eq, ns, tq.shape[0])
+        _check(self._lib.hlm_solve_restart(self._h, t0, tf, _p(tq), tq.shape[0]))
+        self._keep.append(tq)
+
     def solve_window(self, q_hi: int, want_dense: bool = True):
         _check(self._lib.hlm_solve_window(self._h, q_hi, 1 if want_dense else 0))
 
@@ -281,6 +290,14 @@ class Solver:
         v = _D()
         _check(self._lib.hlm_measure_fma_peak(self._h, bits, C.byref(v)))
         return v.value
+
+
+    def debug_eval(self, op: int, x, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if y is None else y, dtype=np.float64), x.shape))
+        out = np.zeros_like(x)
+        _check(self._lib.hlm_debug_eval(self._h, op, _p(x), _p(y), _p(out), x.size))
+        return out
 
 
 # ---- reference-named free functions (process-global default solver, like the reference's globals) ----

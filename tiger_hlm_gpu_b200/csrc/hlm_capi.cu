@@ -171,6 +171,21 @@ __global__ void init_state_kernel(const double* __restrict__ y0_aos, int n_eq, l
     n_acc[i] = n_rej[i] = n_jump[i] = 0u;
 }
 
+// new interval from the resident final states: what a second run_rk45 call with y0 = previous
+// final does, without the host round trip.  Links that did not finish stay flagged.
+__global__ void restart_state_kernel(long long ld, double* __restrict__ t, double* __restrict__ h, int* next_q,
+                                     int* reject_run, int* status, double t0, double h0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    if (status[i] == hlm::kDone || status[i] == hlm::kActive) {
+        t[i] = t0;
+        h[i] = h0;
+        next_q[i] = 0;
+        reject_run[i] = 0;
+        status[i] = hlm::kActive;
+    }
+}
+
 // final states back to the caller's [link][state] order; unfinished links give zeros
 __global__ void gather_final_kernel(const double* __restrict__ y, const int* __restrict__ status, int n_eq,
                                     long long ns, long long ld, double* __restrict__ out_aos) {
@@ -215,6 +230,22 @@ template <typename T> __global__ void fma_peak_kernel(T* out, int iters, T seed)
         }
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// Element-wise probes of device arithmetic, for tests that compare it with the host's.
+__global__ void probe_kernel(int op, const double* __restrict__ x, const double* __restrict__ y,
+                             double* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    switch (op) {
+    case 0: r = pow(x[i], y[i]); break;
+    case 1: asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x[i])); break;
+    case 2: r = __ddiv_rn(x[i], y[i]); break;
+    case 3: r = __dsqrt_rn(x[i]); break;
+    default: r = 0.0;
+    }
+    out[i] = r;
 }
 
 template <class Model> int prepare_params(hlm_ctx* c) {
@@ -527,6 +558,29 @@ int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double 
     return HLM_OK;
 }
 
+int hlm_solve_restart(hlm_ctx* c, double t0, double tf, const double* tq, long long nq) {
+    HLM_REQUIRE(c, "hlm_solve_restart: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_restart: no session (call hlm_solve_begin)");
+    HLM_REQUIRE(nq >= 0 && nq < (1LL << 31) && (nq == 0 || tq), "hlm_solve_restart: bad query times");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(c->tq.reserve((size_t)std::max<long long>(nq, 1)));
+    if (nq > 0) HLM_CUDA(cudaMemcpyAsync(c->tq.p, tq, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, c->stream));
+    const int tpb = 256;
+    // padding lanes beyond ns carry status kDone from init and are re-armed here; the window kernel
+    // never touches them (sys >= ns), so that is harmless
+    restart_state_kernel<<<(unsigned)((c->ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+        c->ld, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p, t0, c->params[c->uid].initialStep);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    c->t0 = t0;
+    c->tf = tf;
+    c->nq = nq;
+    c->q_done = 0;
+    c->win_q_lo = c->win_q_hi = 0;
+    c->win_has_dense = false;
+    return HLM_OK;
+}
+
 int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     HLM_REQUIRE(c, "hlm_solve_window: ctx is NULL");
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_window: no session (call hlm_solve_begin)");
@@ -714,6 +768,24 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
         }
     }
     return hlm_solve_end(c, out_final, out_stiff, out_acc, out_rej, out_jump);
+}
+
+int hlm_debug_eval(hlm_ctx* c, int op, const double* x, const double* y, double* out, long long n) {
+    HLM_REQUIRE(c && x && y && out && n > 0 && op >= 0 && op <= 3, "hlm_debug_eval: bad argument");
+    if (int r = use_device(c)) return r;
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    HLM_CUDA(cudaMalloc(&dx, sizeof(double) * n));
+    HLM_CUDA(cudaMalloc(&dy, sizeof(double) * n));
+    HLM_CUDA(cudaMalloc(&dout, sizeof(double) * n));
+    HLM_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    HLM_CUDA(cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(op, dx, dy, dout, n);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    HLM_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return HLM_OK;
 }
 
 int hlm_measure_fma_peak(hlm_ctx* c, int bits, double* tflops) {
