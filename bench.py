@@ -251,7 +251,11 @@ def main():
 
     sp, col, ncells, pr, t2m, y0 = make_inputs(ns, args.days, args.wet_fraction, rank)
     solver = hlm.Solver(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the library treats handle 0 as "use my own stream", and torch
+    # events only see the stream they are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     solver.set_stream(stream.cuda_stream)
     solver.set_precision(args.precision)
     solver.set_model_parameters(204, hlm.Parameters(*PRM6))

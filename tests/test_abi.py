@@ -32,7 +32,7 @@ def test_binding_covers_the_header():
 def test_abi_version_and_model_registry():
     lib = hlm.load_library()
     assert lib.hlm_abi_version() == hlm.ABI_VERSION
-    assert hlm.model_info(204) == (5, 11, 2)   # Model204::N_EQ = 5 (models/model_204.hpp:19)
+    assert hlm.model_info(204) == (5, 15, 2)   # Model204::N_EQ = 5 (models/model_204.hpp:19)
     assert hlm.model_info(0) == (5, 0, 0)
     with pytest.raises(hlm.HlmError, match="unknown model uid"):
         hlm.model_info(200)

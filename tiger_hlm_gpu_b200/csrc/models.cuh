@@ -27,14 +27,18 @@ static_assert(sizeof(SpatialParamsAoS) == 136, "must match the reference's 136-b
 // Arithmetic follows models/model_204.hpp:54-113 operation by operation, with the two
 // contractions nvcc makes in the reference build (`d1 - s*Emax`, `d2 - h_surf*w`) written as fma.
 // Hoisted out of rhs because they depend on parameters only and are correctly rounded, hence
-// identical whenever computed: 1.0/n_mann (rcp.rn) and sqrt(slope) (sqrt.rn).
+// identical whenever computed: 1.0/n_mann (rcp.rn) and sqrt(slope) (sqrt.rn); and the Newton-refined
+// reciprocals of the four constant divisors (fp_exact.cuh, div_recip/div_by).
+// min_a/max_a take the operand that cannot be NaN first (a parameter, a constant, or a product of
+// forcing and parameter), so a NaN in the state is dropped exactly as fmin/fmax drop it.
 // ---------------------------------------------------------------------------------------------
 struct Model204 {
     static constexpr int UID = 204;
     static constexpr int N_EQ = 5;
-    static constexpr int N_SP = 11;
+    static constexpr int N_SP = 15;
     static constexpr int N_FORC = 2;
-    enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR };
+    enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR,
+           R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };  // R_* = fp<double>::div_recip of the divisor
 
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS& s, double* out) {
         out[INFIL] = s.infil;
@@ -48,6 +52,10 @@ struct Model204 {
         out[ALPHA4] = s.alpha4;
         out[MELT_F] = s.melt_f;
         out[TEMP_THR] = s.temp_thr;
+        out[R_HU] = fp<double>::div_recip(s.Hu);
+        out[R_A_H] = fp<double>::div_recip(s.A_h);
+        out[R_ALPHA3] = fp<double>::div_recip(s.alpha3);
+        out[R_ALPHA4] = fp<double>::div_recip(s.alpha4);
     }
 
     template <typename T> struct Link {
@@ -65,36 +73,36 @@ struct Model204 {
         const T rainfall = F[0], temperature = F[1];
 
         // 1) snow
-        const T snowmelt = (temperature >= P.p[TEMP_THR]) ? f::min(h_snow, f::mul(temperature, P.p[MELT_F])) : (T)0;
+        const T snowmelt = (temperature >= P.p[TEMP_THR]) ? f::min_a(f::mul(temperature, P.p[MELT_F]), h_snow) : (T)0;
         const T x1 = f::add(rainfall, snowmelt);
         dydt[0] = f::sub(rainfall, snowmelt);
 
         // 2) static
-        const T x2 = f::max((T)0, f::sub(f::add(x1, h_stat), P.p[HU]));
+        const T x2 = f::max_a((T)0, f::sub(f::add(x1, h_stat), P.p[HU]));
         const T d1 = f::sub(x1, x2);
-        const T Emax = f::min(f::mul((T)0.1, temperature), h_stat);
-        const T s = f::div(h_stat, P.p[HU]);
+        const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
+        const T s = f::div_by(h_stat, P.p[HU], P.p[R_HU]);
         dydt[1] = f::fma(-s, Emax, d1);
 
         // 3) surface.  When h_surf is +-0 the reference's expression collapses exactly:
         // pow(+-0, 2/3) = +0, so w is 0 (or 1 if L/A_h make a NaN, which fmin drops) and
         // fma(-h_surf, w, d2) adds a signed zero to d2 >= +0, i.e. returns d2 bit for bit.
         // Skipping pow/div there is a warp-divergent but exact shortcut.
-        const T x3 = f::min(x2, P.p[INFIL]);
+        const T x3 = f::min_a(P.p[INFIL], x2);
         const T d2 = f::sub(x2, x3);
         if (h_surf == (T)0) {
             dydt[2] = d2;
         } else {
             const T alfa2 = f::mul(f::mul(P.p[INV_N], f::pow(h_surf, (T)(2.0 / 3.0))), P.p[SQRT_SLOPE]);
-            const T w = f::min((T)1, f::mul(f::div(f::mul(alfa2, P.p[LEN]), P.p[A_H]), (T)60));
+            const T w = f::min_a((T)1, f::mul(f::div_by(f::mul(alfa2, P.p[LEN]), P.p[A_H], P.p[R_A_H]), (T)60));
             dydt[2] = f::fma(-h_surf, w, d2);
         }
 
         // 4) gravitational (interflow), 5) aquifer (baseflow)
-        const T x4 = f::min(x3, P.p[PERCO]);
+        const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
-        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::div(h_grav, P.p[ALPHA3]) : (T)0);
-        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div(h_aq, P.p[ALPHA4]) : (T)0);
+        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::div_by(h_grav, P.p[ALPHA3], P.p[R_ALPHA3]) : (T)0);
+        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div_by(h_aq, P.p[ALPHA4], P.p[R_ALPHA4]) : (T)0);
     }
 };
 

@@ -33,29 +33,75 @@ namespace hlm {
 
 // Dormand–Prince tableau, same expressions as solver/rk45_step_dense.cuh:54-83 so the constants
 // round identically.  Zero entries are kept: the reference multiplies through them and with a
-// non-finite slope that matters (0*inf = NaN).
+// non-finite slope that matters (0*inf = NaN).  The tables live in __constant__ memory: with every
+// loop unrolled the indices are literals and DMUL/DFMA read them as c[bank][offset] operands, with
+// no UMOV pair per use (ncu: 105 UMOVs per attempt when they were immediates).
 namespace dp {
-__device__ constexpr double A[7][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {1.0 / 5.0, 0, 0, 0, 0, 0},
-    {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},
-    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},
-    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},
-    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},
-    {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
-__device__ constexpr double B[7] = {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0,
-                                    -2187.0 / 6784.0, 11.0 / 84.0, 0.0};
-__device__ constexpr double BALT[7] = {5179.0 / 57600.0, 0.0, 7571.0 / 16695.0, 393.0 / 640.0,
-                                       -92097.0 / 339200.0, 187.0 / 2100.0, 1.0 / 40.0};
+#define HLM_DP_A                                                                                 \
+    {{0, 0, 0, 0, 0, 0},                                                                         \
+     {1.0 / 5.0, 0, 0, 0, 0, 0},                                                                 \
+     {3.0 / 40.0, 9.0 / 40.0, 0, 0, 0, 0},                                                       \
+     {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0, 0, 0},                                           \
+     {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0, 0},              \
+     {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0},     \
+     {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}}
+#define HLM_DP_B {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0, 0.0}
+#define HLM_DP_BALT \
+    {5179.0 / 57600.0, 0.0, 7571.0 / 16695.0, 393.0 / 640.0, -92097.0 / 339200.0, 187.0 / 2100.0, 1.0 / 40.0}
 // solver/rk45_step_dense.cuh:193-219
-__device__ constexpr double P[7][4] = {
-    {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},
-    {0.0, 0.0, 0.0, 0.0},
-    {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},
-    {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},
-    {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},
-    {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},
-    {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}};
+#define HLM_DP_P                                                                                                        \
+    {{1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0},                   \
+     {0.0, 0.0, 0.0, 0.0},                                                                                              \
+     {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0},              \
+     {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0},                   \
+     {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0},           \
+     {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0},                        \
+     {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0}}
+constexpr double hA[7][6] = HLM_DP_A;
+constexpr double hB[7] = HLM_DP_B;
+constexpr double hBALT[7] = HLM_DP_BALT;
+constexpr double hP[7][4] = HLM_DP_P;
+struct Tab64 {
+    double A[7][6];
+    double E[7];  // b - b_alt, the compile-time difference the reference's constant folding produces
+    double B6;
+    double P[7][4];
+};
+struct Tab32 {
+    float A[7][6];
+    float E[7];
+    float B6;
+    float P[7][4];
+};
+#define HLM_E(s) (hB[s] - hBALT[s])
+#define HLM_TAB_INIT(T)                                                                                             \
+    {                                                                                                               \
+        {{(T)hA[0][0], (T)hA[0][1], (T)hA[0][2], (T)hA[0][3], (T)hA[0][4], (T)hA[0][5]},                            \
+         {(T)hA[1][0], (T)hA[1][1], (T)hA[1][2], (T)hA[1][3], (T)hA[1][4], (T)hA[1][5]},                            \
+         {(T)hA[2][0], (T)hA[2][1], (T)hA[2][2], (T)hA[2][3], (T)hA[2][4], (T)hA[2][5]},                            \
+         {(T)hA[3][0], (T)hA[3][1], (T)hA[3][2], (T)hA[3][3], (T)hA[3][4], (T)hA[3][5]},                            \
+         {(T)hA[4][0], (T)hA[4][1], (T)hA[4][2], (T)hA[4][3], (T)hA[4][4], (T)hA[4][5]},                            \
+         {(T)hA[5][0], (T)hA[5][1], (T)hA[5][2], (T)hA[5][3], (T)hA[5][4], (T)hA[5][5]},                            \
+         {(T)hA[6][0], (T)hA[6][1], (T)hA[6][2], (T)hA[6][3], (T)hA[6][4], (T)hA[6][5]}},                           \
+            {(T)HLM_E(0), (T)HLM_E(1), (T)HLM_E(2), (T)HLM_E(3), (T)HLM_E(4), (T)HLM_E(5), (T)HLM_E(6)}, (T)hB[6], \
+        {                                                                                                           \
+            {(T)hP[0][0], (T)hP[0][1], (T)hP[0][2], (T)hP[0][3]}, {(T)hP[1][0], (T)hP[1][1], (T)hP[1][2], (T)hP[1][3]}, \
+                {(T)hP[2][0], (T)hP[2][1], (T)hP[2][2], (T)hP[2][3]},                                               \
+                {(T)hP[3][0], (T)hP[3][1], (T)hP[3][2], (T)hP[3][3]},                                               \
+                {(T)hP[4][0], (T)hP[4][1], (T)hP[4][2], (T)hP[4][3]},                                               \
+                {(T)hP[5][0], (T)hP[5][1], (T)hP[5][2], (T)hP[5][3]},                                               \
+                {(T)hP[6][0], (T)hP[6][1], (T)hP[6][2], (T)hP[6][3]}                                                \
+        }                                                                                                           \
+    }
+__constant__ Tab64 c64 = HLM_TAB_INIT(double);
+__constant__ Tab32 c32 = HLM_TAB_INIT(float);
+template <typename T> struct tab;
+template <> struct tab<double> {
+    static __device__ __forceinline__ const Tab64& get() { return c64; }
+};
+template <> struct tab<float> {
+    static __device__ __forceinline__ const Tab32& get() { return c32; }
+};
 }  // namespace dp
 
 // solver/event_detector.cuh:11,15
@@ -113,11 +159,12 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
                                            T (&y6)[Model::N_EQ], T (&y_next)[Model::N_EQ]) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
+    const auto& TB = dp::tab<T>::get();
 #pragma unroll
     for (int s = 1; s < 7; ++s) {
         T ha[6];
 #pragma unroll
-        for (int j = 0; j < s; ++j) ha[j] = f::mul(h, (T)dp::A[s][j]);
+        for (int j = 0; j < s; ++j) ha[j] = f::mul(h, TB.A[s][j]);
         T yt[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -135,20 +182,20 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
     // y_out = y + sum_{s<7} (h*b[s])*k[s].  a[6][j] == b[j] bit for bit for j < 6, so the first six
     // terms ARE y6; only the last (zero-weight) term remains.
     {
-        const T hb6 = f::mul(h, (T)dp::B[6]);
+        const T hb6 = f::mul(h, TB.B6);
 #pragma unroll
         for (int i = 0; i < N; ++i) y_next[i] = f::fma(hb6, k[6][i], y6[i]);
     }
     T he[7];
 #pragma unroll
-    for (int s = 0; s < 7; ++s) he[s] = f::mul(h, (T)(dp::B[s] - dp::BALT[s]));
+    for (int s = 0; s < 7; ++s) he[s] = f::mul(h, TB.E[s]);
     T max_ratio = (T)0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         T e = (T)0;
 #pragma unroll
         for (int s = 0; s < 7; ++s) e = f::fma(he[s], k[s][i], e);
-        const T ymax = f::max(f::abs(y[i]), f::abs(y_next[i]));
+        const T ymax = f::max_a(f::abs(y[i]), f::abs(y_next[i]));  // y NaN => y_next NaN: same result as fmax
         const T tol = f::fma(rtol, ymax, atol);
         const T ratio = f::abs(f::div(e, tol));
         if (ratio > max_ratio) max_ratio = ratio;  // NaN-ignoring form of the reference
@@ -251,7 +298,7 @@ __global__ void __launch_bounds__(128, 3) rk45_window_kernel(const WindowArgs a)
                     if (d > jump) jump = d;
                 }
                 if (jump > (T)kSlopeJumpThresh) {
-                    h = f::max(f::mul(h, (T)0.5), h_floor);
+                    h = f::max_a(h_floor, f::mul(h, (T)0.5));
                     ++n_jmp;
                     k0_valid = true;  // same t, y, F
                     continue;
@@ -268,7 +315,7 @@ __global__ void __launch_bounds__(128, 3) rk45_window_kernel(const WindowArgs a)
                         for (int i = 0; i < N; ++i) {
                             T sum = (T)0;
 #pragma unroll
-                            for (int j = 0; j < 7; ++j) sum = f::fma((T)dp::P[j][m], k[j][i], sum);
+                            for (int j = 0; j < 7; ++j) sum = f::fma(dp::tab<T>::get().P[j][m], k[j][i], sum);
                             Q[m][i] = sum;
                         }
                     do {
@@ -306,13 +353,13 @@ __global__ void __launch_bounds__(128, 3) rk45_window_kernel(const WindowArgs a)
                 t = t1;
                 ++n_acc;
                 const T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
-                h = f::mul(h, f::min(f::max(fac, minScale), maxScale));
+                h = f::mul(h, f::min_a(maxScale, f::max_a(minScale, fac)));
             } else {
                 ++reject_run;
                 ++n_rej;
                 T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
-                fac = f::min(fac, (T)1);
-                fac = f::min(f::max(fac, minScale), maxScale);
+                fac = f::min_a((T)1, fac);
+                fac = f::min_a(maxScale, f::max_a(minScale, fac));
                 h = f::mul(h, fac);
                 k0_valid = true;  // same t, y, F
                 if (reject_run > 5 || h < h_stiff) { status = kStiff; break; }  // rk45_kernel.cu:160-162
