@@ -199,7 +199,7 @@ def run_reference_arm(args):
         "unit": "accepted system-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, ns_sample),
+        "config": dict(workload_config(args, args.links_per_gpu), sample_links_per_step=ns_sample),
         "cpu_baseline": {"value": value, "unit": "accepted system-steps/s", "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "accepted system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -304,13 +304,9 @@ def main():
     state = dict(tot1)
     solver.solve_end()
 
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([acc, attempts, launches, kern_ms, kern_n], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_max = float(t_ms.item())
-    acc_all, att_all, launches_all, kern_ms_all, kern_n_all = [float(x) for x in sums.tolist()]
+    from tiger_hlm_gpu_b200.sharding import reduce_timing
+    ms_max, (acc_all, att_all, launches_all, kern_ms_all, kern_n_all) = reduce_timing(
+        ms, [acc, attempts, launches, kern_ms, kern_n], dist, dev)
     value = acc_all / (ms_max * 1e-3)
 
     # ---------------- end-to-end arm: `e2e` ----------------
@@ -352,15 +348,11 @@ def main():
         # the call is synchronous at its end (results are in host memory), so wall clock and the event
         # pair bracket the same work; report the larger
         e_ms = max(ee0.elapsed_time(ee1), wall_ms)
-        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-        se = torch.tensor([float(acc_e)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(se, op=dist.ReduceOp.SUM)
+        e_ms_max, (acc_e_all,) = reduce_timing(e_ms, [acc_e], dist, dev)
         h2d = ns * 5 * 8 + nq_w * 8
         d2h = ns * 5 * 8 + ns * nq_w * 5 * 8 + ns * 4 + ns * 4
-        e2e = {"value": float(se.item()) / (float(te.item()) * 1e-3), "unit": "accepted system-steps/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) / K,
+        e2e = {"value": acc_e_all / (e_ms_max * 1e-3), "unit": "accepted system-steps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / K,
                "api": "hlm_run_rk45 (C ABI under rk45_api::run_rk45<Model204>), pinned host buffers"}
 
     # ---------------- baselines (rank 0, N == 1 only) ----------------

@@ -1,0 +1,39 @@
+"""The C++ host path end to end: hlm_example (loadSpatialParams -> run_rk45<Model204> shim -> CSV writers)
+against the oracle and the reference's golden, through the same files a reference user would read."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tiger_hlm_gpu_b200 import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXAMPLE = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host", "build", "hlm_example")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(EXAMPLE), reason="hlm_example not built")]
+
+
+def test_cpp_example_writes_reference_format_csvs(tmp_path, small_test_params, golden204):
+    r = subprocess.run([EXAMPLE, os.path.join(GOLDEN, "small_test.csv"), str(tmp_path), "2", "60"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    final = np.loadtxt(tmp_path / "final.csv", delimiter=",", skiprows=1)
+    hdr = open(tmp_path / "dense.csv").readline().strip().split(",")
+    assert hdr[0] == "time" and hdr[1] == "var0_sys0" and hdr[-1] == "var4_sys9" and len(hdr) == 51
+    assert open(tmp_path / "final.csv").readline().strip() == "h_snow,var1,var2,var3,var4"
+    dense = np.loadtxt(tmp_path / "dense.csv", delimiter=",", skiprows=1)
+    assert dense.shape == (49, 51) and np.array_equal(dense[:, 0], np.arange(0, 2881, 60.0))
+    sp = small_test_params
+    ns = len(sp)
+    y0 = np.tile(synthetic.Y0_204, (ns, 1))
+    pr = np.full((48, ns), 0.001, np.float32)
+    t2m = np.full((2, ns), 1.0, np.float32)
+    o = O.run_rk45(204, O.Params.make(initialStep=1e-6), y0, 0.0, 2880.0, np.arange(0, 2881, 60.0), sp=sp,
+                   forcing=O.Forcing([pr, t2m], [1.0, 24.0]), device_pow=True)
+    np.testing.assert_allclose(final, o["final"], rtol=2e-6)            # final.csv holds 6 significant digits
+    got = dense[:, 1:].reshape(49, ns, 5).transpose(1, 0, 2)
+    np.testing.assert_allclose(got, o["dense"], rtol=2e-9, atol=5e-10)   # dense.csv: setprecision(9) fixed
+    tol = 10 * (1e-9 + 1e-6 * np.abs(golden204["final"]))
+    assert np.all(np.abs(final - golden204["final"]) <= tol + 2e-6 * np.abs(golden204["final"]))

@@ -24,7 +24,8 @@ class HlmError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libhlm_b200.so")
+    # HLM_B200_LIB selects another build of the same library (kernel-tuning experiments)
+    return os.environ.get("HLM_B200_LIB") or os.path.join(_HERE, "libhlm_b200.so")
 
 
 _lib = None

@@ -758,9 +758,11 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
     } else {
         const long long per_q = ns * c->n_eq * (long long)sizeof(double);
         long long qw = std::max<long long>(1, c->dense_window_bytes / per_q);
-        // the last window also runs to tf; keep windows even so the tail is not a sliver
-        const long long n_win = (nq + qw - 1) / qw;
-        qw = (nq + n_win - 1) / n_win;
+        long long n_win = (nq + qw - 1) / qw;
+        // a large transfer is cut into at least 6 windows so that all but the last window's D2H copy
+        // overlaps the next window's integration (two buffers, copy stream)
+        if (per_q * nq > (256LL << 20)) n_win = std::max<long long>(n_win, std::min<long long>(6, nq));
+        qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
         for (long long q = 0; q < nq;) {
             q = std::min(nq, q + qw);
             if (int r = hlm_solve_window(c, q, 1)) return r;

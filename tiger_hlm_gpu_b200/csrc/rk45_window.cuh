@@ -29,6 +29,9 @@
 #include "fp_exact.cuh"
 #include "models.cuh"
 
+#ifndef HLM_BLOCKS_PER_SM
+#define HLM_BLOCKS_PER_SM 3
+#endif
 namespace hlm {
 
 // Dormand–Prince tableau, same expressions as solver/rk45_step_dense.cuh:54-83 so the constants
@@ -217,7 +220,7 @@ __device__ __forceinline__ long long forcing_index(double t, double dt_min, long
 }
 
 template <class Model, typename T>
-__global__ void __launch_bounds__(128, 3) rk45_window_kernel(const WindowArgs a) {
+__global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const int lane = threadIdx.x & 31;
