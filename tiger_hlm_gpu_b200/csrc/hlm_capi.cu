@@ -243,6 +243,7 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
     case 1: asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x[i])); break;
     case 2: r = __ddiv_rn(x[i], y[i]); break;
     case 3: r = __dsqrt_rn(x[i]); break;
+    case 4: r = hlm::fp<double>::pow_pos(x[i], y[i]); break;
     default: r = 0.0;
     }
     out[i] = r;
@@ -773,7 +774,7 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
 }
 
 int hlm_debug_eval(hlm_ctx* c, int op, const double* x, const double* y, double* out, long long n) {
-    HLM_REQUIRE(c && x && y && out && n > 0 && op >= 0 && op <= 3, "hlm_debug_eval: bad argument");
+    HLM_REQUIRE(c && x && y && out && n > 0 && op >= 0 && op <= 4, "hlm_debug_eval: bad argument");
     if (int r = use_device(c)) return r;
     double *dx = nullptr, *dy = nullptr, *dout = nullptr;
     HLM_CUDA(cudaMalloc(&dx, sizeof(double) * n));

@@ -66,8 +66,14 @@ struct Model204 {
         }
     };
 
-    template <typename T>
-    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt) {
+    /// true when every hoisted reciprocal is usable (divisors inside div_recip's exponent range)
+    template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) {
+        return P.p[R_HU] == P.p[R_HU] && P.p[R_A_H] == P.p[R_A_H] && P.p[R_ALPHA3] == P.p[R_ALPHA3] &&
+               P.p[R_ALPHA4] == P.p[R_ALPHA4];
+    }
+
+    template <typename T, bool kFast>
+    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, bool& bad) {
         using f = fp<T>;
         const T h_snow = y[0], h_stat = y[1], h_surf = y[2], h_grav = y[3], h_aq = y[4];
         const T rainfall = F[0], temperature = F[1];
@@ -81,7 +87,7 @@ struct Model204 {
         const T x2 = f::max_a((T)0, f::sub(f::add(x1, h_stat), P.p[HU]));
         const T d1 = f::sub(x1, x2);
         const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
-        const T s = f::div_by(h_stat, P.p[HU], P.p[R_HU]);
+        const T s = f::template div_by<kFast>(h_stat, P.p[HU], P.p[R_HU], bad);
         dydt[1] = f::fma(-s, Emax, d1);
 
         // 3) surface.  When h_surf is +-0 the reference's expression collapses exactly:
@@ -93,16 +99,16 @@ struct Model204 {
         if (h_surf == (T)0) {
             dydt[2] = d2;
         } else {
-            const T alfa2 = f::mul(f::mul(P.p[INV_N], f::pow(h_surf, (T)(2.0 / 3.0))), P.p[SQRT_SLOPE]);
-            const T w = f::min_a((T)1, f::mul(f::div_by(f::mul(alfa2, P.p[LEN]), P.p[A_H], P.p[R_A_H]), (T)60));
+            const T alfa2 = f::mul(f::mul(P.p[INV_N], f::pow_pos(h_surf, (T)(2.0 / 3.0))), P.p[SQRT_SLOPE]);
+            const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.p[LEN]), P.p[A_H], P.p[R_A_H], bad), (T)60));
             dydt[2] = f::fma(-h_surf, w, d2);
         }
 
         // 4) gravitational (interflow), 5) aquifer (baseflow)
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
-        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::div_by(h_grav, P.p[ALPHA3], P.p[R_ALPHA3]) : (T)0);
-        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div_by(h_aq, P.p[ALPHA4], P.p[R_ALPHA4]) : (T)0);
+        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::template div_by<kFast>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad) : (T)0);
+        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::template div_by<kFast>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad) : (T)0);
     }
 };
 
@@ -121,8 +127,9 @@ struct DummyModel {
     template <typename T> struct Link {
         __device__ __forceinline__ void load(const double*, long long, long long) {}
     };
-    template <typename T>
-    static __device__ __forceinline__ void rhs(const T* y, const T*, const Link<T>&, T* dydt) {
+    template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>&) { return true; }
+    template <typename T, bool kFast>
+    static __device__ __forceinline__ void rhs(const T* y, const T*, const Link<T>&, T* dydt, bool&) {
         using f = fp<T>;
         const T Y0 = f::mul((T)0.5, y[0]);
         const T X2 = f::mul((T)0.3, y[1]);

@@ -156,10 +156,10 @@ struct StepOut {
 
 // One DOPRI5 attempt from (y, k0): fills k[1..6], y6 (stage-6 state), y_next, returns err.
 // solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
-template <class Model, typename T>
+template <class Model, typename T, bool kFast>
 __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][Model::N_EQ], T h,
                                            const T* F, const typename Model::template Link<T>& L, T rtol, T atol,
-                                           T (&y6)[Model::N_EQ], T (&y_next)[Model::N_EQ]) {
+                                           T (&y6)[Model::N_EQ], T (&y_next)[Model::N_EQ], bool& bad) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const auto& TB = dp::tab<T>::get();
@@ -176,7 +176,7 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
             for (int j = 0; j < s; ++j) acc = f::fma(ha[j], k[j][i], acc);
             yt[i] = acc;
         }
-        Model::template rhs<T>(yt, F, L, k[s]);
+        Model::template rhs<T, kFast>(yt, F, L, k[s], bad);
         if (s == 6) {
 #pragma unroll
             for (int i = 0; i < N; ++i) y6[i] = yt[i];
@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         unsigned int n_acc = a.n_accept[sys], n_rej = a.n_reject[sys], n_jmp = a.n_jump[sys];
         typename Model::template Link<T> L;
         L.load(a.sp, a.ld, sys);
+        const bool fast_ok = Model::template fast_div_ok<T>(L);
         const long long col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
 
         T F[2] = {(T)0, (T)0};
@@ -288,8 +289,19 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                 }
             }
 
-            if (!k0_valid) Model::template rhs<T>(y, F, L, k[0]);  // rk45_kernel.cu:114
-            const T err = dopri_attempt<Model, T>(y, k, h, F, L, rtol, atol, y6, y_next);
+            // Fast attempt: constant-divisor divisions without guards, `bad` collects any operand that
+            // needs the real div.rn.f64; then (rarely) the attempt is redone with exact divisions.
+            bool bad = !fast_ok;
+            T err;
+            if (!bad) {
+                if (!k0_valid) Model::template rhs<T, true>(y, F, L, k[0], bad);  // rk45_kernel.cu:114
+                err = dopri_attempt<Model, T, true>(y, k, h, F, L, rtol, atol, y6, y_next, bad);
+            }
+            if (bad) {
+                bool unused = false;
+                Model::template rhs<T, false>(y, F, L, k[0], unused);
+                err = dopri_attempt<Model, T, false>(y, k, h, F, L, rtol, atol, y6, y_next, unused);
+            }
 
             if (err <= (T)1) {
                 reject_run = 0;
@@ -355,12 +367,12 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                 k0_valid = fsal;
                 t = t1;
                 ++n_acc;
-                const T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
+                const T fac = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
                 h = f::mul(h, f::min_a(maxScale, f::max_a(minScale, fac)));
             } else {
                 ++reject_run;
                 ++n_rej;
-                T fac = f::mul(safety, f::pow(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
+                T fac = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
                 fac = f::min_a((T)1, fac);
                 fac = f::min_a(maxScale, f::max_a(minScale, fac));
                 h = f::mul(h, fac);
