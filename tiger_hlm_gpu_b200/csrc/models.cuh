@@ -58,19 +58,29 @@ struct Model204 {
         out[R_ALPHA4] = fp<double>::div_recip(s.alpha4);
     }
 
+    // Per-link constants held in registers for a whole window.  The five columns only the surface
+    // (h_surf != 0) branch reads — INV_N, SQRT_SLOPE, LEN, A_H, R_A_H — are NOT kept: that branch
+    // re-reads them through the read-only path (L1 hits), which frees 10 registers on a kernel that
+    // sits at the 168-register cap of 3 CTAs/SM.
     template <typename T> struct Link {
-        T p[N_SP];
-        __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld, long long sys) {
+        T p[N_SP];  // wet-only slots stay unused (dead registers are eliminated)
+        const double* wet;  // &sp[0][sys]
+        long long ld;
+        bool recips_ok;
+        __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld_, long long sys) {
+            const int dry[] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, MELT_F, TEMP_THR, R_HU, R_ALPHA3, R_ALPHA4};
 #pragma unroll
-            for (int i = 0; i < N_SP; ++i) p[i] = (T)__ldg(sp + (long long)i * ld + sys);
+            for (int i = 0; i < 10; ++i) p[dry[i]] = (T)__ldg(sp + (long long)dry[i] * ld_ + sys);
+            wet = sp + sys;
+            ld = ld_;
+            const double ra = __ldg(sp + (long long)R_A_H * ld_ + sys);
+            recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
         }
+        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + (long long)c * ld); }
     };
 
     /// true when every hoisted reciprocal is usable (divisors inside div_recip's exponent range)
-    template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) {
-        return P.p[R_HU] == P.p[R_HU] && P.p[R_A_H] == P.p[R_A_H] && P.p[R_ALPHA3] == P.p[R_ALPHA3] &&
-               P.p[R_ALPHA4] == P.p[R_ALPHA4];
-    }
+    template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) { return P.recips_ok; }
 
     template <typename T, bool kFast>
     static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, bool& bad) {
@@ -99,8 +109,9 @@ struct Model204 {
         if (h_surf == (T)0) {
             dydt[2] = d2;
         } else {
-            const T alfa2 = f::mul(f::mul(P.p[INV_N], f::pow_pos(h_surf, (T)(2.0 / 3.0))), P.p[SQRT_SLOPE]);
-            const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.p[LEN]), P.p[A_H], P.p[R_A_H], bad), (T)60));
+            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::pow_pos(h_surf, (T)(2.0 / 3.0))), P.wet_param(SQRT_SLOPE));
+            const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
+                                                                      P.wet_param(R_A_H), bad), (T)60));
             dydt[2] = f::fma(-h_surf, w, d2);
         }
 

@@ -154,12 +154,12 @@ struct StepOut {
     T err;
 };
 
-// One DOPRI5 attempt from (y, k0): fills k[1..6], y6 (stage-6 state), y_next, returns err.
+// One DOPRI5 attempt from (y, k0): fills k[1..6], y_next and the FSAL flag, returns err.
 // solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
 template <class Model, typename T, bool kFast>
 __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][Model::N_EQ], T h,
                                            const T* F, const typename Model::template Link<T>& L, T rtol, T atol,
-                                           T (&y6)[Model::N_EQ], T (&y_next)[Model::N_EQ], bool& bad) {
+                                           T (&y_next)[Model::N_EQ], bool& fsal, bool& bad) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const auto& TB = dp::tab<T>::get();
@@ -178,16 +178,17 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
         }
         Model::template rhs<T, kFast>(yt, F, L, k[s], bad);
         if (s == 6) {
+            // y_out = y + sum_{s<7} (h*b[s])*k[s].  a[6][j] == b[j] bit for bit for j < 6, so the first
+            // six terms ARE the stage-6 state yt; only the last (zero-weight) term remains.  FSAL: k6 =
+            // rhs(yt, F) is the next k0 iff y_next == yt bit for bit (that term changed nothing).
+            const T hb6 = f::mul(h, TB.B6);
+            fsal = true;
 #pragma unroll
-            for (int i = 0; i < N; ++i) y6[i] = yt[i];
+            for (int i = 0; i < N; ++i) {
+                y_next[i] = f::fma(hb6, k[6][i], yt[i]);
+                fsal = fsal && f::same_bits(y_next[i], yt[i]);
+            }
         }
-    }
-    // y_out = y + sum_{s<7} (h*b[s])*k[s].  a[6][j] == b[j] bit for bit for j < 6, so the first six
-    // terms ARE y6; only the last (zero-weight) term remains.
-    {
-        const T hb6 = f::mul(h, TB.B6);
-#pragma unroll
-        for (int i = 0; i < N; ++i) y_next[i] = f::fma(hb6, k[6][i], y6[i]);
     }
     T he[7];
 #pragma unroll
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         if (status != kActive) continue;
 
         // ---- load lane state (coalesced columns) ----
-        T y[N], k[7][N], y6[N], y_next[N];
+        T y[N], k[7][N], y_next[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) y[i] = (T)a.y[(long long)i * a.ld + sys];
         T t = (T)a.t[sys], h = (T)a.h[sys];
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         double f_lo = fp<double>::inf(), f_hi = -fp<double>::inf();  // empty validity interval
         T tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
         bool k0_valid = false;
-        long long budget = a.max_attempts;
+        int budget = (a.max_attempts > 0x7fffffffLL) ? 0x7fffffff : (int)a.max_attempts;
 
         for (;;) {
             if (!(t < tf)) { status = kDone; break; }
@@ -291,17 +292,20 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
 
             // Fast attempt: constant-divisor divisions without guards, `bad` collects any operand that
             // needs the real div.rn.f64; then (rarely) the attempt is redone with exact divisions.
-            bool bad = !fast_ok;
+            bool bad = !fast_ok, fsal = false;
             T err;
             if (!bad) {
                 if (!k0_valid) Model::template rhs<T, true>(y, F, L, k[0], bad);  // rk45_kernel.cu:114
-                err = dopri_attempt<Model, T, true>(y, k, h, F, L, rtol, atol, y6, y_next, bad);
+                err = dopri_attempt<Model, T, true>(y, k, h, F, L, rtol, atol, y_next, fsal, bad);
             }
-            if (bad) {
+            if (__builtin_expect(bad, 0)) {
                 bool unused = false;
                 Model::template rhs<T, false>(y, F, L, k[0], unused);
-                err = dopri_attempt<Model, T, false>(y, k, h, F, L, rtol, atol, y6, y_next, unused);
+                err = dopri_attempt<Model, T, false>(y, k, h, F, L, rtol, atol, y_next, fsal, unused);
             }
+            // step-size factor of the controller, needed on both the accept and the reject branch
+            // (rk45_kernel.cu:151,156): one inlined pow instead of two
+            const T fac0 = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
 
             if (err <= (T)1) {
                 reject_run = 0;
@@ -354,11 +358,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                 }
                 if (overshoot) break;  // step spans past this window's buffer: leave it uncommitted, redo next window
 
-                // FSAL: k6 = rhs(y6, F).  It is the next k0 iff y_next == y6 bit for bit (the zero-weight
-                // b[6] term changed nothing) and the forcing sample is unchanged (checked next iteration).
-                bool fsal = true;
-#pragma unroll
-                for (int i = 0; i < N; ++i) fsal = fsal && f::same_bits(y_next[i], y6[i]);
+                // FSAL (see dopri_attempt); the forcing sample must also be unchanged (checked next iteration)
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     y[i] = y_next[i];
@@ -367,13 +367,11 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                 k0_valid = fsal;
                 t = t1;
                 ++n_acc;
-                const T fac = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
-                h = f::mul(h, f::min_a(maxScale, f::max_a(minScale, fac)));
+                h = f::mul(h, f::min_a(maxScale, f::max_a(minScale, fac0)));
             } else {
                 ++reject_run;
                 ++n_rej;
-                T fac = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
-                fac = f::min_a((T)1, fac);
+                T fac = f::min_a((T)1, fac0);
                 fac = f::min_a(maxScale, f::max_a(minScale, fac));
                 h = f::mul(h, fac);
                 k0_valid = true;  // same t, y, F
