@@ -201,7 +201,7 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
         for (int s = 0; s < 7; ++s) e = f::fma(he[s], k[s][i], e);
         const T ymax = f::max_a(f::abs(y[i]), f::abs(y_next[i]));  // y NaN => y_next NaN: same result as fmax
         const T tol = f::fma(rtol, ymax, atol);
-        const T ratio = f::abs(f::div(e, tol));
+        const T ratio = f::abs(f::template div_err<kFast>(e, tol, bad));
         if (ratio > max_ratio) max_ratio = ratio;  // NaN-ignoring form of the reference
     }
     return max_ratio;
