@@ -243,7 +243,12 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
     case 1: asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x[i])); break;
     case 2: r = __ddiv_rn(x[i], y[i]); break;
     case 3: r = __dsqrt_rn(x[i]); break;
-    case 4: r = hlm::fp<double>::pow_pos(x[i], y[i]); break;
+    case 4: {  // the kernels' fast pow with its fallback, as the solver uses it
+        bool bad = false;
+        r = hlm::fp<double>::pow_pos<true>(x[i], y[i], bad);
+        if (bad) r = hlm::fp<double>::pow_pos<false>(x[i], y[i], bad);
+        break;
+    }
     default: r = 0.0;
     }
     out[i] = r;

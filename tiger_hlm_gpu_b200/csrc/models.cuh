@@ -109,7 +109,7 @@ struct Model204 {
         if (h_surf == (T)0) {
             dydt[2] = d2;
         } else {
-            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::pow_pos(h_surf, (T)(2.0 / 3.0))), P.wet_param(SQRT_SLOPE));
+            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::template pow_pos<kFast>(h_surf, (T)(2.0 / 3.0), bad)), P.wet_param(SQRT_SLOPE));
             const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
                                                                       P.wet_param(R_A_H), bad), (T)60));
             dydt[2] = f::fma(-h_surf, w, d2);

@@ -292,20 +292,21 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
 
             // Fast attempt: constant-divisor divisions without guards, `bad` collects any operand that
             // needs the real div.rn.f64; then (rarely) the attempt is redone with exact divisions.
+            // fac0 = safety * pow(1/(err + 1e-16), 0.2): the controller's factor, needed on both the
+            // accept and the reject branch (rk45_kernel.cu:151,156), so computed once here.
             bool bad = !fast_ok, fsal = false;
-            T err;
+            T err, fac0;
             if (!bad) {
                 if (!k0_valid) Model::template rhs<T, true>(y, F, L, k[0], bad);  // rk45_kernel.cu:114
                 err = dopri_attempt<Model, T, true>(y, k, h, F, L, rtol, atol, y_next, fsal, bad);
+                fac0 = f::mul(safety, f::template pow_pos<true>(f::template rcp_pos<true>(f::add(err, (T)1e-16), bad), (T)0.2, bad));
             }
             if (__builtin_expect(bad, 0)) {
                 bool unused = false;
                 Model::template rhs<T, false>(y, F, L, k[0], unused);
                 err = dopri_attempt<Model, T, false>(y, k, h, F, L, rtol, atol, y_next, fsal, unused);
+                fac0 = f::mul(safety, f::template pow_pos<false>(f::rcp(f::add(err, (T)1e-16)), (T)0.2, unused));
             }
-            // step-size factor of the controller, needed on both the accept and the reject branch
-            // (rk45_kernel.cu:151,156): one inlined pow instead of two
-            const T fac0 = f::mul(safety, f::pow_pos(f::rcp(f::add(err, (T)1e-16)), (T)0.2));
 
             if (err <= (T)1) {
                 reject_run = 0;
