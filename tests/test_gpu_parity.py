@@ -348,3 +348,35 @@ def test_restart_equals_chained_run_rk45(solver):
     r = solver.solve_end()
     assert np.array_equal(r["final"], chained[-1]["final"])
     assert np.array_equal(r["n_accept"], sum(c["n_accept"] for c in chained))
+
+
+def test_unusual_parameters_take_the_exact_fallback(solver):
+    """Links whose divisors or states leave the fast paths' ranges (alpha < 1, alpha huge, zero or
+    negative storages, Hu tiny) must still match the oracle bit for bit via the exact redo."""
+    ns, days = 96, 1
+    sp = synthetic.make_spatial_params(ns)
+    sp["alpha3"][0:8] = 0.5          # < 1: term is 0 (model_204.hpp:109)
+    sp["alpha4"][8:16] = 0.0
+    sp["alpha3"][16:24] = 1e300      # reciprocal out of range -> exact division
+    sp["Hu"][24:32] = 1e-30
+    sp["alpha4"][32:40] = 1.0
+    sp["Hu"][40:48] = 3.5            # saturation excess: h_surf becomes positive on its own
+    col, ncells = synthetic.make_cells(ns, links_per_cell=16)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days)
+    y0 = synthetic.make_y0(ns, 0.5)
+    y0[48:56, 3] = 0.0               # zero numerator of h_grav / alpha3
+    y0[56:64, 4] = 0.0
+    y0[64:72, 1] = 1e-320            # subnormal numerator of h_stat / Hu
+    y0[72:80, 3] = -1e-3             # negative storage
+    solver.set_model_parameters(204, PRM)
+    solver.set_max_attempts(2_000_000)
+    solver.upload_spatial_params(sp)
+    solver.clear_forcings()
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(col)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    g = solver.run_rk45(204, y0, 0.0, tf, tq)
+    o = orun(204, OPRM, y0, 0.0, tf, tq, sp=sp, forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col), threads=8)
+    assert_same_result(g, o, exact=True)

@@ -54,8 +54,11 @@ struct Model204 {
         out[TEMP_THR] = s.temp_thr;
         out[R_HU] = fp<double>::div_recip(s.Hu);
         out[R_A_H] = fp<double>::div_recip(s.A_h);
-        out[R_ALPHA3] = fp<double>::div_recip(s.alpha3);
-        out[R_ALPHA4] = fp<double>::div_recip(s.alpha4);
+        // The reference drains these stores only when alpha >= 1 (model_204.hpp:109,112), else the term
+        // is 0.  A zero "reciprocal" makes the three-instruction quotient exactly +-0 for every finite
+        // numerator, so the fast path needs no select; the exact path keeps the comparison.
+        out[R_ALPHA3] = (s.alpha3 >= 1.0) ? fp<double>::div_recip(s.alpha3) : 0.0;
+        out[R_ALPHA4] = (s.alpha4 >= 1.0) ? fp<double>::div_recip(s.alpha4) : 0.0;
     }
 
     // Per-link constants held in registers for a whole window.  The five columns only the surface
@@ -118,8 +121,13 @@ struct Model204 {
         // 4) gravitational (interflow), 5) aquifer (baseflow)
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
-        dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::template div_by<kFast>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad) : (T)0);
-        dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::template div_by<kFast>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad) : (T)0);
+        if (kFast && sizeof(T) == 8) {
+            dydt[3] = f::sub(d3, f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad));
+            dydt[4] = f::sub(x4, f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad));
+        } else {
+            dydt[3] = f::sub(d3, (P.p[ALPHA3] >= (T)1) ? f::div(h_grav, P.p[ALPHA3]) : (T)0);
+            dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div(h_aq, P.p[ALPHA4]) : (T)0);
+        }
     }
 };
 
