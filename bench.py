@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--wet-fraction", type=float, default=0.0,
                     help="share of links started with surface storage so Model204's pow() branch runs")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
+    ap.add_argument("--rtol", type=float, default=None, help="override rtol (default 1e-6)")
+    ap.add_argument("--atol", type=float, default=None, help="override atol (default 1e-9)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference_cuda legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
@@ -221,6 +223,10 @@ def workload_config(args, ns):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    if args.rtol is not None:
+        PRM6[1] = args.rtol
+    if args.atol is not None:
+        PRM6[2] = args.atol
     if args.impl == "reference":
         run_reference_arm(args)
         return
