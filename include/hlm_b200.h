@@ -96,6 +96,14 @@ int hlm_upload_spatial_params(hlm_ctx* ctx, const void* aos, long long n, long l
  * GRID (ncols = lat*lon cells) and link s reads column col[s] = lat_index*lon_size + lon_index
  * (main.cpp:501-505); the per-link expansion is never materialised. */
 int hlm_upload_forcing(hlm_ctx* ctx, int j, double dt_hours, long long nT, long long ncols, const float* data);
+/* The same with only samples [i0, i0 + nT_chunk) of an nT_total-sample record resident: the
+ * time-chunked loading of I_O/forcing_loader.cpp:165-196 (NetCDFLoader::loadTimeChunk) carried to the
+ * device.  Indexing and clamping stay those of the whole record; hlm_solve_window fails with
+ * HLM_ERR_STATE when the resident chunk does not cover the interval being integrated.  The upload is
+ * ordered after the windows already queued, so the next interval's chunk can be sent while the host
+ * writes the previous one's output. */
+int hlm_upload_forcing_chunk(hlm_ctx* ctx, int j, double dt_hours, long long nT_total, long long i0,
+                             long long nT_chunk, long long ncols, const float* data);
 int hlm_set_forcing_columns(hlm_ctx* ctx, const int* col, long long n);
 int hlm_clear_forcings(hlm_ctx* ctx);
 
@@ -149,6 +157,17 @@ int hlm_solve_window_buffer(hlm_ctx* ctx, void** dev_ptr, long long* q_lo, long 
 /* Copy the last window's dense records into the full host array [ns][nq][N_EQ]. Asynchronous if
  * `host_dense` is pinned. */
 int hlm_solve_fetch_window(hlm_ctx* ctx, double* host_dense);
+/* Copy the last window's dense records packed as [ns][q_hi - q_lo][N_EQ] (the feed of a windowed file
+ * writer).  Asynchronous on the copy stream if `host_win` is pinned; `ticket` (may be NULL) names the
+ * copy for hlm_solve_wait_copy(), which blocks until that copy has landed (ticket < 0: all queued
+ * copies) and may be called from another host thread.  The reference copies the whole dense array with
+ * one blocking cudaMemcpy after the run (solver/rk45_api.hpp:173-196). */
+int hlm_solve_fetch_window_packed(hlm_ctx* ctx, double* host_win, int* ticket);
+int hlm_solve_wait_copy(hlm_ctx* ctx, int ticket);
+/* Page-locked host memory for those copies (cudaHostAlloc / cudaFreeHost without linking the CUDA
+ * runtime into the host program). */
+int hlm_host_alloc(void** out, long long bytes);
+int hlm_host_free(void* p);
 /* Sums over links, computed on the device: {accepted, rejected, slope-jump, unfinished-active,
  * done, stiff, stalled}.  Synchronises. */
 int hlm_solve_totals(hlm_ctx* ctx, long long totals[7]);

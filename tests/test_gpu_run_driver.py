@@ -1,0 +1,206 @@
+"""End-to-end run driver (tiger_hlm_gpu_b200/host/hlm_run.cpp) on a B200: config.yaml + parameters CSV +
+lookup CSV + forcing NetCDF in, final/dense NetCDF out — the reference's main() flow (main.cpp:314-823)
+for this path.  Outputs must equal, bit for bit, the same run driven through the Python mirror of the
+C ABI and the CPU oracle chained over the same day-sized intervals."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+import tiger_hlm_gpu_b200 as hlm
+from tiger_hlm_gpu_b200 import hostio
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host")
+RUN = os.path.join(HOST, "build", "hlm_run")
+COLS = ["stream", "next_stream", "i2", "i3", "hu", "centroid_lat", "sw", "ss", "n", "slope", "length_km",
+        "drainage_area_km2", "melt", "t_thres", "res_ss", "res_gw"]
+NLAT, NLON, DAYS, NS = 3, 4, 3, 203
+
+
+def write_case(d, world_dirs=True):
+    rng = np.random.default_rng(11)
+    os.makedirs(d / "params"), os.makedirs(d / "forc"), os.makedirs(d / "out")
+    stream = 420000000 + np.arange(NS)
+    rows = np.column_stack([
+        stream, stream + 1, np.full(NS, 4.0), np.full(NS, 1.6), rng.uniform(150, 200, NS), rng.uniform(38, 42, NS),
+        np.full(NS, 0.11), np.full(NS, 0.33), np.full(NS, 0.1), np.full(NS, 0.02), rng.uniform(0.09, 2.1, NS),
+        np.exp(rng.uniform(np.log(0.13), np.log(1.6), NS)), np.full(NS, 3.7), np.zeros(NS), np.full(NS, 2.0), np.full(NS, 55.0)])
+    with open(d / "params" / "links.csv", "w") as f:
+        f.write(",".join(COLS) + "\n")
+        for r in rows:
+            f.write(",".join([str(int(r[0])), str(int(r[1]))] + [repr(float(x)) for x in r[2:]]) + "\n")
+    lat_i, lon_i = rng.integers(0, NLAT, NS), rng.integers(0, NLON, NS)
+    with open(d / "forc" / "lookup.csv", "w") as f:
+        f.write("stream,lat_index,lon_index\n")
+        for s, a, b in zip(stream, lat_i, lon_i):
+            f.write(f"{s},{a},{b}\n")
+    # heavy enough rain that some links pond water (the pow() branch) without going stiff
+    wet = rng.random((DAYS * 24, NLAT, NLON)) < 0.3
+    pr = (np.where(wet, rng.exponential(2.0, wet.shape), 0.0) * (0.001 / 60.0) * 8.0).astype(np.float32)
+    t2m = (5.0 + 6.0 * rng.standard_normal((DAYS, NLAT, NLON))).astype(np.float32)
+    with netcdf_file(str(d / "forc" / "a_pr_hourly.nc"), "w", version=2) as f:
+        f.createDimension("time", None), f.createDimension("latitude", NLAT), f.createDimension("longitude", NLON)
+        tv = f.createVariable("time", "i4", ("time",))
+        tv.units = "hours since 2021-01-01 00:00:00"
+        tv[:] = np.arange(DAYS * 24)
+        f.createVariable("PRCP", "f4", ("time", "latitude", "longitude"))[:] = pr
+    with netcdf_file(str(d / "forc" / "b_t2m_daily.nc"), "w", version=1) as f:  # no time coordinate: dt falls back to 24 h
+        f.createDimension("time", DAYS), f.createDimension("latitude", NLAT), f.createDimension("longitude", NLON)
+        f.createVariable("Tair", "f4", ("time", "latitude", "longitude"))[:] = t2m
+    return pr.reshape(DAYS * 24, -1), t2m.reshape(DAYS, -1), (lat_i * NLON + lon_i).astype(np.int32)
+
+
+def config_text(start, end, origin=None, mode="cold", init_file="", states="[0, 2, 4]", prefix=""):
+    origin_line = f'  origin: "{origin}"\n' if origin else ""
+    init_line = f'  file: "{init_file}"\n' if mode == "hot" else ""
+    return f"""\
+model:
+  uid: 204
+  name: Model204
+time:
+  start: "{start}"
+  end:   "{end}"
+{origin_line}initial:
+  mode: {mode}
+{init_line}local_params:
+  file: "params/links.csv"
+forcings:
+  type:    folder_nc
+  path:    "forc"
+  lookup:  "lookup.csv"
+  vars:
+    precipitation: "PRCP"
+    temperature:   "Tair"
+output:
+  print_interval: "1h"
+  states: {states}
+  dir: "out"
+  prefix: "{prefix}"
+solver:
+  method: RK45
+  tolerances:
+    rtol:      1e-6
+    atol:      1e-9
+    safety:    0.9
+    min_scale: 0.2
+    max_scale: 10.0
+  initial_step: null
+  max_attempts: 2000000
+mpi:
+  step_storage: 30
+  transfer_buffer: 10
+  discontinuity_buf: 0
+"""
+
+
+def run_driver(d, cfg_name, world=1):
+    subprocess.check_call(["make", "-C", HOST, "build/hlm_run"], stdout=subprocess.DEVNULL)
+    for r in range(world):
+        out = subprocess.run([RUN, str(d / cfg_name), "--rank", str(r), "--world", str(world), "--device", "0"],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "done:" in out.stdout
+
+
+def read_nc(path):
+    with netcdf_file(str(path), "r", mmap=False) as f:
+        return {k: np.array(v[:]) for k, v in f.variables.items()}
+
+
+def expected(sp, col, pr, t2m, day_lo, day_hi, y0):
+    """The same run through the Python mirror of the C ABI, one interval per day (hlm_solve_restart keeps
+    links that were flagged stiff flagged, exactly what the driver's session does)."""
+    ns = len(sp)
+    dense = np.zeros((ns, (day_hi - day_lo) * 24 + 1, 5))
+    with hlm.Solver(0) as s:
+        s.set_model_parameters(204, hlm.Parameters(initialStep=1e-6))
+        s.set_max_attempts(2_000_000)
+        s.upload_spatial_params(sp)
+        s.upload_forcing(0, 1.0, pr)
+        s.upload_forcing(1, 24.0, t2m)
+        s.set_forcing_columns(col)
+        for k in range(day_lo, day_hi):
+            tq = k * 1440.0 + 60.0 * np.arange(1, 25)
+            if k == day_lo:  # the first interval also owns the (never written, F10) query at its start
+                tq = np.concatenate([[k * 1440.0], tq])
+                s.solve_begin(204, y0, k * 1440.0, (k + 1) * 1440.0, tq)
+            else:
+                s.solve_restart(k * 1440.0, (k + 1) * 1440.0, tq)
+            s.solve_window(len(tq))
+            win = np.zeros((ns, len(tq), 5))
+            s.solve_fetch_window(win)
+            s.synchronize()
+            q0 = (k - day_lo) * 24 + (0 if k == day_lo else 1)
+            dense[:, q0:q0 + len(tq)] = win
+        r = s.solve_end()
+    return r["final"], dense, r["stiff"]
+
+
+def test_driver_two_ranks_matches_python_api_and_oracle(tmp_path):
+    pr, t2m, col = write_case(tmp_path)
+    (tmp_path / "config.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-04T00:00:00"))
+    run_driver(tmp_path, "config.yaml", world=2)
+    sp_all = hostio.load_spatial_params(str(tmp_path / "params" / "links.csv"))
+    from tiger_hlm_gpu_b200.sharding import shard_range
+    y0c = np.tile([0.01, 3.0, 0.0, 5.0, 0.2], (NS, 1))
+    saw_wet = False
+    for rank in range(2):
+        lo, hi = shard_range(NS, 2, rank)
+        fin = read_nc(tmp_path / "out" / f"final_rank_{rank}.nc")
+        den = read_nc(tmp_path / "out" / f"dense_rank_{rank}.nc")
+        assert np.array_equal(fin["system"], sp_all["stream"][lo:hi])      # real link ids
+        assert np.array_equal(den["variable"], [0, 2, 4])                  # output.states
+        assert np.array_equal(den["time"], 60.0 * np.arange(DAYS * 24 + 1))
+        y, dense, stiff = expected(sp_all[lo:hi], col[lo:hi], pr, t2m, 0, DAYS, y0c[lo:hi])
+        assert np.array_equal(fin["outputs"], y)
+        assert np.array_equal(den["outputs"], dense[:, :, [0, 2, 4]])
+        assert not den["outputs"][:, 0].any()                              # t = t0 is never written
+        saw_wet |= bool((dense[:, :, 2] > 0).any())
+        if rank == 0:  # and the CPU oracle, chained the same way (links it never flags stiff)
+            yo = y0c[lo:hi]
+            ok = np.ones(hi - lo, bool)
+            for k in range(DAYS):
+                o = O.run_rk45(204, O.Params.make(initialStep=1e-6), yo, k * 1440.0, (k + 1) * 1440.0,
+                               k * 1440.0 + 60.0 * np.arange(1, 25), sp=sp_all[lo:hi],
+                               forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col[lo:hi]), threads=os.cpu_count() or 1,
+                               device_pow=True)
+                ok &= o["stiff"] == 0
+                assert np.array_equal(o["dense"][ok], dense[ok, 1 + 24 * k:25 + 24 * k])
+                yo = o["final"]
+            assert np.array_equal(yo[ok], y[ok]) and np.array_equal(~ok, stiff != 0) and ok.sum() > 50
+    assert saw_wet, "the case was meant to exercise the surface-storage branch"
+
+
+def test_driver_hot_start_continues_a_run(tmp_path):
+    """Days 1-2, then day 3 restarted from the final-state file: same states as the uninterrupted run."""
+    pr, t2m, col = write_case(tmp_path)
+    (tmp_path / "full.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-04T00:00:00", states="[0, 1, 2, 3, 4]", prefix="full_"))
+    (tmp_path / "a.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-03T00:00:00", states="[0, 1, 2, 3, 4]", prefix="a_"))
+    (tmp_path / "b.yaml").write_text(config_text("2021-01-03T00:00:00", "2021-01-04T00:00:00", origin="2021-01-01T00:00:00", mode="hot",
+                                                 init_file="out/a_final_rank_0.nc", states="[0, 1, 2, 3, 4]", prefix="b_"))
+    for c in ("full.yaml", "a.yaml", "b.yaml"):
+        run_driver(tmp_path, c)
+    full_f, full_d = read_nc(tmp_path / "out" / "full_final_rank_0.nc"), read_nc(tmp_path / "out" / "full_dense_rank_0.nc")
+    b_f, b_d = read_nc(tmp_path / "out" / "b_final_rank_0.nc"), read_nc(tmp_path / "out" / "b_dense_rank_0.nc")
+    # links flagged stiff during days 1-2 have no final state (zero rows, solver/rk45_kernel.cu:167-170):
+    # the uninterrupted run keeps them flagged, a restart would start them from zeros
+    a_f = read_nc(tmp_path / "out" / "a_final_rank_0.nc")
+    ok = a_f["outputs"].any(axis=1)
+    assert 50 < ok.sum() < NS
+    assert np.array_equal(b_f["system"], full_f["system"])
+    assert np.array_equal(b_f["outputs"][ok], full_f["outputs"][ok])
+    assert np.array_equal(b_d["time"], 2880.0 + 60.0 * np.arange(25))
+    assert np.array_equal(b_d["outputs"][ok, 1:], full_d["outputs"][ok, 49:])
+
+
+def test_driver_reports_errors_like_main(tmp_path):
+    write_case(tmp_path)
+    (tmp_path / "bad.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-02T00:00:00").replace('"PRCP"', '"nope"'))
+    subprocess.check_call(["make", "-C", HOST, "build/hlm_run"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([RUN, str(tmp_path / "bad.yaml")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "nope" in out.stderr

@@ -15,7 +15,7 @@ from dataclasses import dataclass, astuple
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "hlm_get_model_parameters": (_I, [_V, _I, _V]),
     "hlm_upload_spatial_params": (_I, [_V, _V, _LL, _LL]),
     "hlm_upload_forcing": (_I, [_V, _I, _D, _LL, _LL, _V]),
+    "hlm_upload_forcing_chunk": (_I, [_V, _I, _D, _LL, _LL, _LL, _LL, _V]),
     "hlm_set_forcing_columns": (_I, [_V, _V, _LL]),
     "hlm_clear_forcings": (_I, [_V]),
     "hlm_set_max_attempts": (_I, [_V, _LL]),
@@ -56,6 +57,10 @@ SIGNATURES = {
     "hlm_solve_window": (_I, [_V, _LL, _I]),
     "hlm_solve_window_buffer": (_I, [_V, C.POINTER(_V), C.POINTER(_LL), C.POINTER(_LL)]),
     "hlm_solve_fetch_window": (_I, [_V, _V]),
+    "hlm_solve_fetch_window_packed": (_I, [_V, _V, C.POINTER(_I)]),
+    "hlm_solve_wait_copy": (_I, [_V, _I]),
+    "hlm_host_alloc": (_I, [C.POINTER(_V), _LL]),
+    "hlm_host_free": (_I, [_V]),
     "hlm_solve_totals": (_I, [_V, _V]),
     "hlm_solve_end": (_I, [_V, _V, _V, _V, _V, _V]),
     "hlm_solve_peek": (_I, [_V, _V, _V, _V]),
@@ -189,6 +194,13 @@ class Solver:
         _check(self._lib.hlm_upload_forcing(self._h, j, dt_hours, data.shape[0], data.shape[1], _p(data)))
         self._keep.append(data)
 
+    def upload_forcing_chunk(self, j: int, dt_hours: float, nT_total: int, i0: int, data: np.ndarray):
+        """Samples [i0, i0 + len(data)) of an nT_total-sample record (time-chunked residency)."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        assert data.ndim == 2, "forcing chunk is [nT_chunk][ncols]"
+        _check(self._lib.hlm_upload_forcing_chunk(self._h, j, dt_hours, nT_total, i0, data.shape[0], data.shape[1], _p(data)))
+        self._keep.append(data)
+
     def set_forcing_columns(self, col):
         if col is None:
             _check(self._lib.hlm_set_forcing_columns(self._h, None, 0))
@@ -254,6 +266,16 @@ class Solver:
     def solve_fetch_window(self, host_dense: np.ndarray):
         assert host_dense.dtype == np.float64 and host_dense.flags.c_contiguous
         _check(self._lib.hlm_solve_fetch_window(self._h, _p(host_dense)))
+
+    def solve_fetch_window_packed(self, host_win: np.ndarray) -> int:
+        """Last window packed as [ns][q_hi - q_lo][N_EQ]; returns the ticket for solve_wait_copy."""
+        assert host_win.dtype == np.float64 and host_win.flags.c_contiguous
+        t = _I()
+        _check(self._lib.hlm_solve_fetch_window_packed(self._h, _p(host_win), C.byref(t)))
+        return t.value
+
+    def solve_wait_copy(self, ticket: int = -1):
+        _check(self._lib.hlm_solve_wait_copy(self._h, ticket))
 
     def solve_fetch_window_ptr(self, host_ptr: int):
         _check(self._lib.hlm_solve_fetch_window(self._h, _V(host_ptr)))

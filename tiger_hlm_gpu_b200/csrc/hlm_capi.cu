@@ -96,7 +96,9 @@ struct hlm_ctx {
 
     // forcings
     DevBuf<float> forc[2];
-    long long forc_nT[2] = {0, 0};
+    long long forc_nT[2] = {0, 0};    // whole record
+    long long forc_i0[2] = {0, 0};    // first resident sample
+    long long forc_nres[2] = {0, 0};  // resident samples
     long long forc_ncols = 0;
     double forc_dt_h[2] = {0, 0};
     int n_forc = 0;
@@ -316,7 +318,7 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
 // =================================================================================================
 extern "C" {
 
-int hlm_abi_version(void) { return 1; }
+int hlm_abi_version(void) { return 2; }
 
 const char* hlm_last_error(void) { return g_err.c_str(); }
 
@@ -427,23 +429,33 @@ int hlm_upload_spatial_params(hlm_ctx* c, const void* aos, long long n, long lon
     return HLM_OK;
 }
 
-int hlm_upload_forcing(hlm_ctx* c, int j, double dt_hours, long long nT, long long ncols, const float* data) {
+int hlm_upload_forcing_chunk(hlm_ctx* c, int j, double dt_hours, long long nT_total, long long i0, long long nT_chunk,
+                             long long ncols, const float* data) {
     HLM_REQUIRE(c && data, "hlm_upload_forcing: NULL argument");
     HLM_REQUIRE(j >= 0 && j < hlm::kMaxForcings, "hlm_upload_forcing: forcing index out of range [0,16)");
-    HLM_REQUIRE(nT > 0 && ncols > 0, "hlm_upload_forcing: nT and ncols must be positive");
+    HLM_REQUIRE(nT_total > 0 && ncols > 0, "hlm_upload_forcing: nT and ncols must be positive");
+    HLM_REQUIRE(i0 >= 0 && nT_chunk > 0 && i0 + nT_chunk <= nT_total, "hlm_upload_forcing_chunk: chunk outside the record");
     if (j >= 2) return HLM_OK;  // accepted like the reference's 16 slots, but no compiled model reads F[j>=2]
     HLM_REQUIRE(j <= c->n_forc, "hlm_upload_forcing: upload forcings in order 0,1,...");
     for (int k = 0; k < c->n_forc; ++k)
         if (k != j && c->forc_ncols != ncols)
             return fail(HLM_ERR_INVALID, "hlm_upload_forcing: all forcings must share ncols");
     if (int r = use_device(c)) return r;
-    HLM_CUDA(c->forc[j].reserve((size_t)nT * ncols));
-    HLM_CUDA(cudaMemcpyAsync(c->forc[j].p, data, sizeof(float) * (size_t)nT * ncols, cudaMemcpyHostToDevice, c->stream));
-    c->forc_nT[j] = nT;
+    // a larger chunk reallocates: the window kernels queued on the stream must be done with the old buffer
+    if ((size_t)nT_chunk * ncols > c->forc[j].cap) HLM_CUDA(cudaStreamSynchronize(c->stream));
+    HLM_CUDA(c->forc[j].reserve((size_t)nT_chunk * ncols));
+    HLM_CUDA(cudaMemcpyAsync(c->forc[j].p, data, sizeof(float) * (size_t)nT_chunk * ncols, cudaMemcpyHostToDevice, c->stream));
+    c->forc_nT[j] = nT_total;
+    c->forc_i0[j] = i0;
+    c->forc_nres[j] = nT_chunk;
     c->forc_dt_h[j] = dt_hours;
     c->forc_ncols = ncols;
     if (j == c->n_forc) c->n_forc = j + 1;
     return HLM_OK;
+}
+
+int hlm_upload_forcing(hlm_ctx* c, int j, double dt_hours, long long nT, long long ncols, const float* data) {
+    return hlm_upload_forcing_chunk(c, j, dt_hours, nT, 0, nT, ncols, data);
 }
 
 int hlm_set_forcing_columns(hlm_ctx* c, const int* col, long long n) {
@@ -593,6 +605,20 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     if (int r = use_device(c)) return r;
     if (q_hi > c->nq) q_hi = c->nq;
     HLM_REQUIRE(q_hi >= c->q_done, "hlm_solve_window: q_hi must not move backwards");
+    // a chunked forcing record must cover every sample the interval [t0, tf] can index
+    // (size_t(t / (dt*60)) clamped to the record, solver/rk45_kernel.cu:90-98)
+    if (const ModelInfo* m = find_model(c->uid))
+        for (int j = 0; j < std::min(c->n_forc, m->n_forc); ++j) {
+            const double dtm = c->forc_dt_h[j] * 60.0;
+            if (!(dtm > 0.0) || c->forc_nres[j] == c->forc_nT[j]) continue;
+            auto index = [&](double t) {
+                const double r = t / dtm;
+                return (r < 0.0) ? 0LL : (r >= (double)c->forc_nT[j] ? c->forc_nT[j] - 1 : (long long)r);
+            };
+            if (index(c->t0) < c->forc_i0[j] || index(c->tf) >= c->forc_i0[j] + c->forc_nres[j])
+                return fail(HLM_ERR_STATE, "hlm_solve_window: the resident chunk of forcing " + std::to_string(j) +
+                                               " does not cover the interval");
+        }
     const long long q_lo = c->q_done;
     const long long qw = q_hi - q_lo;
     const bool dense = want_dense && qw > 0;
@@ -618,6 +644,8 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     for (int j = 0; j < 2; ++j) {
         a.forc[j] = c->forc[j].p;
         a.forc_nT[j] = c->forc_nT[j];
+        a.forc_i0[j] = c->forc_i0[j];
+        a.forc_nres[j] = c->forc_nres[j];
         a.forc_dt_min[j] = c->forc_dt_h[j] * 60.0;  // rk45_kernel.cu:90
     }
     a.forc_ncols = c->forc_ncols;
@@ -667,6 +695,40 @@ int hlm_solve_fetch_window(hlm_ctx* c, double* host_dense) {
                                    c->copy_stream));
     HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
     c->copy_pending[buf] = true;
+    return HLM_OK;
+}
+
+int hlm_solve_fetch_window_packed(hlm_ctx* c, double* host_win, int* ticket) {
+    HLM_REQUIRE(c && host_win, "hlm_solve_fetch_window_packed: NULL argument");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_fetch_window_packed: no session");
+    if (ticket) *ticket = c->dense_cur;
+    if (!c->win_has_dense) return HLM_OK;
+    if (int r = use_device(c)) return r;
+    const int buf = c->dense_cur;
+    const size_t bytes = (size_t)c->ns * (size_t)(c->win_q_hi - c->win_q_lo) * c->n_eq * sizeof(double);
+    HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
+    HLM_CUDA(cudaMemcpyAsync(host_win, c->dense[buf].p, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
+    c->copy_pending[buf] = true;
+    return HLM_OK;
+}
+
+int hlm_solve_wait_copy(hlm_ctx* c, int ticket) {
+    HLM_REQUIRE(c, "hlm_solve_wait_copy: ctx is NULL");
+    if (int r = use_device(c)) return r;
+    if (ticket == 0 || ticket == 1) HLM_CUDA(cudaEventSynchronize(c->ev_copy_done[ticket]));
+    else HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return HLM_OK;
+}
+
+int hlm_host_alloc(void** out, long long bytes) {
+    HLM_REQUIRE(out && bytes > 0, "hlm_host_alloc: bad argument");
+    HLM_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return HLM_OK;
+}
+
+int hlm_host_free(void* p) {
+    if (p) HLM_CUDA(cudaFreeHost(p));
     return HLM_OK;
 }
 

@@ -133,8 +133,10 @@ struct WindowArgs {
     unsigned int* n_jump;    // [ld]
     const double* sp;      // [N_SP][ld]  model-prepared parameter columns
     const int* col;        // [ld] forcing column (grid cell) per link, or nullptr = link index
-    const float* forc[2];  // forcing j: [nT][ncols]
-    long long forc_nT[2];
+    const float* forc[2];  // forcing j: samples [forc_i0, forc_i0 + forc_nres) of the record, [nres][ncols]
+    long long forc_nT[2];    // length of the whole record (the reference's c_forc_nT: the index clamps to it)
+    long long forc_i0[2];    // first resident sample
+    long long forc_nres[2];  // resident samples
     double forc_dt_min[2];  // c_forc_dt[j] * 60.0, rk45_kernel.cu:90
     long long forc_ncols;
     int n_forc;            // forcings present (0..2 used by the models here)
@@ -280,7 +282,11 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                         if (j < a.n_forc) {
                             double lo, hi;
                             const long long idx = forcing_index(td, a.forc_dt_min[j], a.forc_nT[j], lo, hi);
-                            const T v = (T)__ldg(a.forc[j] + idx * a.forc_ncols + col);  // f32 -> f64 widening as model_204.hpp:82-83
+                            // resident chunk of the record (the host checks that it covers the interval; the
+                            // clamp only keeps a mis-driven run inside the buffer)
+                            long long r = idx - a.forc_i0[j];
+                            r = r < 0 ? 0 : (r >= a.forc_nres[j] ? a.forc_nres[j] - 1 : r);
+                            const T v = (T)__ldg(a.forc[j] + r * a.forc_ncols + col);  // f32 -> f64 widening as model_204.hpp:82-83
                             if (!f::same_bits(v, F[j])) k0_valid = false;
                             F[j] = v;
                             f_lo = fmax(f_lo, lo);

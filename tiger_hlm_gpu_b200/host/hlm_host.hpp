@@ -12,7 +12,7 @@
 
 #include <fstream>
 #include <iomanip>
-#include <iostream>
+#include <cstdio>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -81,7 +81,7 @@ class LookupMapper {
     bool load() {
         std::ifstream file(filepath_);
         if (!file.is_open()) {
-            std::cerr << "Failed to open file: " << filepath_ << std::endl;
+            std::fprintf(stderr, "Failed to open file: %s\n", filepath_.c_str());
             return false;
         }
         std::string line;
