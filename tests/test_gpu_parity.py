@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+import tiger_hlm_gpu_b200 as hlm
 from tiger_hlm_gpu_b200 import Parameters, synthetic
 
 pytestmark = pytest.mark.gpu
@@ -380,3 +381,50 @@ def test_unusual_parameters_take_the_exact_fallback(solver):
     g = solver.run_rk45(204, y0, 0.0, tf, tq)
     o = orun(204, OPRM, y0, 0.0, tf, tq, sp=sp, forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col), threads=8)
     assert_same_result(g, o, exact=True)
+
+
+def test_time_chunked_forcing_equals_resident_record(solver):
+    """hlm_upload_forcing_chunk: only the samples an interval needs are resident; indexing and the
+    clamp at the end of the record stay those of the whole record (solver/rk45_kernel.cu:90-98)."""
+    ns, days = 200, 4
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.2)
+    pr, t2m = forcing.blocks
+    col = forcing.col
+    # reference result: whole record resident, one interval per day, the last one running past the record
+    def drive(upload):
+        out = []
+        for k in range(days + 1):
+            tq = k * 1440.0 + 120.0 * np.arange(1, 13)
+            upload(k)
+            if k == 0:
+                solver.solve_begin(204, y0, 0.0, 1440.0, tq)
+            else:
+                solver.solve_restart(k * 1440.0, (k + 1) * 1440.0, tq)
+            solver.solve_window(12)
+            win = np.zeros((ns, 12, 5))
+            t = solver.solve_fetch_window_packed(win)
+            solver.solve_wait_copy(t)
+            out.append(win)
+        r = solver.solve_end()
+        return np.concatenate(out, axis=1), r
+    d_full, r_full = drive(lambda k: None)
+
+    def upload_chunk(k):  # samples of day k (+ the one the interval's end time indexes), clamped to the record
+        lo = min(k * 24, pr.shape[0] - 1)
+        hi = min((k + 1) * 24, pr.shape[0] - 1)
+        solver.upload_forcing_chunk(0, 1.0, pr.shape[0], lo, pr[lo:hi + 1])
+        lo2 = min(k, t2m.shape[0] - 1)
+        hi2 = min(k + 1, t2m.shape[0] - 1)
+        solver.upload_forcing_chunk(1, 24.0, t2m.shape[0], lo2, t2m[lo2:hi2 + 1])
+    solver.set_forcing_columns(col)
+    d_chunk, r_chunk = drive(upload_chunk)
+    assert np.array_equal(d_chunk, d_full)
+    for key in ("final", "stiff", "n_accept", "n_reject", "n_jump"):
+        assert np.array_equal(r_chunk[key], r_full[key]), key
+    # a chunk that does not cover the interval is refused, not silently clamped
+    solver.upload_forcing_chunk(0, 1.0, pr.shape[0], 30, pr[30:40])
+    solver.solve_begin(204, y0, 0.0, 1440.0, 120.0 * np.arange(1, 13))
+    with pytest.raises(hlm.HlmError, match="does not cover"):
+        solver.solve_window(12)
+    solver.solve_end()
+    solver.clear_forcings()
