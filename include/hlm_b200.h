@@ -50,6 +50,9 @@ typedef enum hlm_status {
 #define HLM_LINK_OK 0
 #define HLM_LINK_STIFF 1
 #define HLM_LINK_STALLED 2
+/* 3 = flagged stiff by the RK45 path, then carried to tf by the implicit fallback of
+ * hlm_set_stiff_fallback(): final state and dense records are valid. */
+#define HLM_LINK_STIFF_SOLVED 3
 
 /* ---- context ------------------------------------------------------------------------------- */
 
@@ -114,6 +117,12 @@ int hlm_set_max_attempts(hlm_ctx* ctx, long long per_link);
 /* Bytes of device memory one dense-output window buffer may take (two are allocated when the run
  * needs more than one window).  Default 8 GiB. */
 int hlm_set_dense_window_bytes(hlm_ctx* ctx, long long bytes);
+/* What happens to a link the RK45 path flags stiff (solver/rk45_kernel.cu:160-170).  0 (default): it is
+ * abandoned, the state of the path in the reference whenever its Radau kernel is left out.  1: after every
+ * window the flagged links are carried on by a 3-stage Radau IIA integrator — the role of
+ * radau_kernel_multi in run_rk45 (solver/rk45_api.hpp:198-247, solver/radau_kernel.cu:20-140), with the
+ * numerics done properly (csrc/radau_fallback.cuh says what was kept and what was replaced).  FP64 only. */
+int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
 /* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */
 int hlm_set_precision(hlm_ctx* ctx, int bits);
 
@@ -174,6 +183,8 @@ int hlm_solve_totals(hlm_ctx* ctx, long long totals[7]);
 /* Download final states and per-link codes/counters (any pointer may be NULL).  Synchronises. */
 int hlm_solve_end(hlm_ctx* ctx, double* out_final, int* out_stiff, long long* out_n_accept,
                   long long* out_n_reject, long long* out_n_jump);
+/* Accepted implicit (Radau) steps per link so far; they are not part of out_n_accept.  Synchronises. */
+int hlm_solve_radau_steps(hlm_ctx* ctx, long long* out_steps);
 /* Download the raw resident state (t, h per link) for inspection/tests.  Either may be NULL. */
 int hlm_solve_peek(hlm_ctx* ctx, double* out_t, double* out_h, double* out_y);
 /* Number of kernel launches issued by this context since creation (bench's gpu_launches). */

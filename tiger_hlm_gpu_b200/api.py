@@ -51,6 +51,8 @@ SIGNATURES = {
     "hlm_set_max_attempts": (_I, [_V, _LL]),
     "hlm_set_dense_window_bytes": (_I, [_V, _LL]),
     "hlm_set_precision": (_I, [_V, _I]),
+    "hlm_set_stiff_fallback": (_I, [_V, _I]),
+    "hlm_solve_radau_steps": (_I, [_V, _V]),
     "hlm_run_rk45": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL, _V, _V, _V, _V, _V, _V]),
     "hlm_solve_begin": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL]),
     "hlm_solve_restart": (_I, [_V, _D, _D, _V, _LL]),
@@ -217,6 +219,15 @@ class Solver:
 
     def set_dense_window_bytes(self, n: int):
         _check(self._lib.hlm_set_dense_window_bytes(self._h, n))
+
+    def set_stiff_fallback(self, enable: bool):
+        """Radau IIA re-integration of links the RK45 path flags stiff (run_rk45's documented behaviour)."""
+        _check(self._lib.hlm_set_stiff_fallback(self._h, 1 if enable else 0))
+
+    def solve_radau_steps(self) -> np.ndarray:
+        out = np.zeros(self._session[2], np.int64)
+        _check(self._lib.hlm_solve_radau_steps(self._h, _p(out)))
+        return out
 
     def set_precision(self, bits: int):
         _check(self._lib.hlm_set_precision(self._h, bits))

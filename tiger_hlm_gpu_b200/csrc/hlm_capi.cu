@@ -19,6 +19,7 @@
 
 #include "../../include/hlm_b200.h"
 #include "rk45_window.cuh"
+#include "radau_fallback.cuh"
 
 namespace {
 
@@ -124,6 +125,11 @@ struct hlm_ctx {
     cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
 
+    // implicit fallback for links the RK45 path flags stiff (radau_fallback.cuh)
+    bool stiff_fallback = false;
+    DevBuf<int> radau_list;
+    DevBuf<unsigned int> radau_count, n_radau;
+
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // per window kernel
     std::vector<cudaEvent_t> event_pool;
@@ -179,7 +185,7 @@ __global__ void restart_state_kernel(long long ld, double* __restrict__ t, doubl
                                      int* reject_run, int* status, double t0, double h0) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ld) return;
-    if (status[i] == hlm::kDone || status[i] == hlm::kActive) {
+    if (status[i] == hlm::kDone || status[i] == hlm::kActive || status[i] == hlm::kDoneStiff) {
         t[i] = t0;
         h[i] = h0;
         next_q[i] = 0;
@@ -193,7 +199,7 @@ __global__ void gather_final_kernel(const double* __restrict__ y, const int* __r
                                     long long ns, long long ld, double* __restrict__ out_aos) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
-    const bool ok = status[i] == hlm::kDone;
+    const bool ok = status[i] == hlm::kDone || status[i] == hlm::kDoneStiff;
     for (int c = 0; c < n_eq; ++c) out_aos[i * n_eq + c] = ok ? y[(long long)c * ld + i] : 0.0;
 }
 
@@ -207,7 +213,7 @@ __global__ void totals_kernel(const unsigned int* __restrict__ n_acc, const unsi
         v[1] += n_rej[i];
         v[2] += n_jump[i];
         const int s = status[i];
-        v[3 + (s < 0 || s > 3 ? 0 : s)] += 1;
+        v[3 + (s == hlm::kDoneStiff ? (int)hlm::kDone : (s == hlm::kStiffPaused ? (int)hlm::kStiff : (s < 0 || s > 3 ? 0 : s)))] += 1;
     }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -304,12 +310,38 @@ template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::Wind
     return 0;
 }
 
+// links flagged stiff by the window kernel just queued -> list -> implicit integration of the same window
+template <class Model> int launch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
+    HLM_CUDA(cudaMemsetAsync(c->radau_count.p, 0, sizeof(unsigned int), c->stream));
+    const int tpb = 256;
+    hlm::radau_collect_kernel<<<(unsigned)((a.ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(a.status, a.ns, c->radau_list.p,
+                                                                                        c->radau_count.p);
+    HLM_CUDA(cudaGetLastError());
+    hlm::RadauArgs ra;
+    ra.w = a;
+    ra.list = c->radau_list.p;
+    ra.n_list = c->radau_count.p;
+    ra.n_radau = c->n_radau.p;
+    // the list length lives on the device: a fixed grid strides over it (flagged links are rare)
+    const unsigned grid = (unsigned)std::min<long long>((a.ns + 63) / 64, (long long)c->sm_count * 4);
+    hlm::radau_window_kernel<Model><<<grid, 64, 0, c->stream>>>(ra);
+    HLM_CUDA(cudaGetLastError());
+    c->launches += 2;
+    return 0;
+}
+
 int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     if (c->uid == hlm::Model204::UID)
         return c->precision == 32 ? launch_window<hlm::Model204, float>(c, a) : launch_window<hlm::Model204, double>(c, a);
     if (c->uid == hlm::DummyModel::UID)
         return c->precision == 32 ? launch_window<hlm::DummyModel, float>(c, a)
                                   : launch_window<hlm::DummyModel, double>(c, a);
+    return fail(HLM_ERR_INVALID, "unknown model uid");
+}
+
+int dispatch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
+    if (c->uid == hlm::Model204::UID) return launch_radau<hlm::Model204>(c, a);
+    if (c->uid == hlm::DummyModel::UID) return launch_radau<hlm::DummyModel>(c, a);
     return fail(HLM_ERR_INVALID, "unknown model uid");
 }
 
@@ -490,6 +522,12 @@ int hlm_set_dense_window_bytes(hlm_ctx* c, long long v) {
     return HLM_OK;
 }
 
+int hlm_set_stiff_fallback(hlm_ctx* c, int enable) {
+    HLM_REQUIRE(c, "hlm_set_stiff_fallback: ctx is NULL");
+    c->stiff_fallback = enable != 0;
+    return HLM_OK;
+}
+
 int hlm_set_precision(hlm_ctx* c, int bits) {
     HLM_REQUIRE(c && (bits == 64 || bits == 32), "hlm_set_precision: bits must be 64 or 32");
     c->precision = bits;
@@ -557,6 +595,10 @@ int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double 
     HLM_CUDA(c->n_jump.reserve(ld));
     HLM_CUDA(c->tile_counter.reserve(1));
     HLM_CUDA(c->totals.reserve(8));
+    HLM_CUDA(c->radau_list.reserve(ld));
+    HLM_CUDA(c->radau_count.reserve(1));
+    HLM_CUDA(c->n_radau.reserve(ld));
+    HLM_CUDA(cudaMemsetAsync(c->n_radau.p, 0, sizeof(unsigned int) * ld, c->stream));
     HLM_CUDA(c->tq.reserve((size_t)std::max<long long>(nq, 1)));
     if (nq > 0) HLM_CUDA(cudaMemcpyAsync(c->tq.p, tq, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, c->stream));
     // y0 arrives [link][state]; stage it in the (not yet used) dense buffer, then transpose to columns
@@ -660,6 +702,8 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     a.max_attempts = c->max_attempts;
     a.tile_counter = c->tile_counter.p;
     if (int r = dispatch_window(c, a)) return r;
+    if (c->stiff_fallback)
+        if (int r = dispatch_radau(c, a)) return r;
     c->q_done = q_hi;
     c->win_q_lo = q_lo;
     c->win_q_hi = q_hi;
@@ -749,6 +793,18 @@ int hlm_solve_totals(hlm_ctx* c, long long totals[7]) {
     return HLM_OK;
 }
 
+int hlm_solve_radau_steps(hlm_ctx* c, long long* out_steps) {
+    HLM_REQUIRE(c && out_steps, "hlm_solve_radau_steps: NULL argument");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_radau_steps: no session");
+    if (int r = use_device(c)) return r;
+    std::vector<unsigned int> tmp;
+    try { tmp.resize((size_t)c->ns); } catch (const std::bad_alloc&) { return fail(HLM_ERR_NOMEM, "hlm_solve_radau_steps: out of host memory"); }
+    HLM_CUDA(cudaMemcpyAsync(tmp.data(), c->n_radau.p, sizeof(unsigned int) * (size_t)c->ns, cudaMemcpyDeviceToHost, c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    for (long long i = 0; i < c->ns; ++i) out_steps[i] = (long long)tmp[(size_t)i];
+    return HLM_OK;
+}
+
 int hlm_solve_peek(hlm_ctx* c, double* out_t, double* out_h, double* out_y) {
     HLM_REQUIRE(c, "hlm_solve_peek: ctx is NULL");
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_peek: no session");
@@ -807,7 +863,8 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
         HLM_CUDA(cudaStreamSynchronize(c->stream));
         for (long long i = 0; i < ns; ++i) {
             const int s = st[(size_t)i];
-            out_stiff[i] = (s == hlm::kStiff) ? HLM_LINK_STIFF : (s == hlm::kDone ? HLM_LINK_OK : HLM_LINK_STALLED);
+            out_stiff[i] = (s == hlm::kStiff || s == hlm::kStiffPaused) ? HLM_LINK_STIFF
+                           : (s == hlm::kDone ? HLM_LINK_OK : (s == hlm::kDoneStiff ? HLM_LINK_STIFF_SOLVED : HLM_LINK_STALLED));
         }
     }
     HLM_CUDA(cudaStreamSynchronize(c->stream));

@@ -111,7 +111,9 @@ template <> struct tab<float> {
 constexpr double kSlopeJumpThresh = 100.0;
 constexpr double kMinStepFraction = 1e-6;
 
-enum LinkStatus : int { kActive = 0, kDone = 1, kStiff = 2, kStalled = 3 };
+// kDoneStiff: flagged stiff by the RK45 path, then carried to tf by the implicit fallback (radau_fallback.cuh);
+// kStiffPaused: in the fallback's hands, waiting for the next output window
+enum LinkStatus : int { kActive = 0, kDone = 1, kStiff = 2, kStalled = 3, kDoneStiff = 4, kStiffPaused = 5 };
 
 constexpr int kMaxForcings = 16;  // I_O/forcing_data.h:5
 
