@@ -19,7 +19,12 @@
 
 #include "../../include/hlm_b200.h"
 #include "rk45_window.cuh"
-#include "radau_fallback.cuh"
+
+// radau_fallback.cu (its own translation unit: built without FMA contraction)
+namespace hlm {
+cudaError_t radau_launch(int uid, const WindowArgs& a, int* list, unsigned int* n_list, unsigned int* n_radau,
+                         int sm_count, cudaStream_t stream);
+}
 
 namespace {
 
@@ -310,26 +315,6 @@ template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::Wind
     return 0;
 }
 
-// links flagged stiff by the window kernel just queued -> list -> implicit integration of the same window
-template <class Model> int launch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
-    HLM_CUDA(cudaMemsetAsync(c->radau_count.p, 0, sizeof(unsigned int), c->stream));
-    const int tpb = 256;
-    hlm::radau_collect_kernel<<<(unsigned)((a.ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(a.status, a.ns, c->radau_list.p,
-                                                                                        c->radau_count.p);
-    HLM_CUDA(cudaGetLastError());
-    hlm::RadauArgs ra;
-    ra.w = a;
-    ra.list = c->radau_list.p;
-    ra.n_list = c->radau_count.p;
-    ra.n_radau = c->n_radau.p;
-    // the list length lives on the device: a fixed grid strides over it (flagged links are rare)
-    const unsigned grid = (unsigned)std::min<long long>((a.ns + 63) / 64, (long long)c->sm_count * 4);
-    hlm::radau_window_kernel<Model><<<grid, 64, 0, c->stream>>>(ra);
-    HLM_CUDA(cudaGetLastError());
-    c->launches += 2;
-    return 0;
-}
-
 int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     if (c->uid == hlm::Model204::UID)
         return c->precision == 32 ? launch_window<hlm::Model204, float>(c, a) : launch_window<hlm::Model204, double>(c, a);
@@ -339,10 +324,11 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     return fail(HLM_ERR_INVALID, "unknown model uid");
 }
 
+// links flagged stiff by the window kernel just queued -> list -> implicit integration of the same window
 int dispatch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
-    if (c->uid == hlm::Model204::UID) return launch_radau<hlm::Model204>(c, a);
-    if (c->uid == hlm::DummyModel::UID) return launch_radau<hlm::DummyModel>(c, a);
-    return fail(HLM_ERR_INVALID, "unknown model uid");
+    HLM_CUDA(hlm::radau_launch(c->uid, a, c->radau_list.p, c->radau_count.p, c->n_radau.p, c->sm_count, c->stream));
+    c->launches += 2;
+    return 0;
 }
 
 }  // namespace

@@ -1,0 +1,37 @@
+// radau_fallback.cu — translation unit of the implicit fallback (radau_fallback.cuh).
+//
+// Built with -fmad=false: its linear algebra is written as plain C++ expressions and must round exactly
+// like the CPU twin the tests compare it with.  The RK45 translation unit keeps nvcc's default (its
+// arithmetic goes through explicit intrinsics, and libdevice's pow must stay the build the reference
+// uses), which is why this is a file of its own.
+#include "radau_fallback.cuh"
+
+namespace hlm {
+
+template <class Model>
+static cudaError_t radau_launch_model(const WindowArgs& a, int* list, unsigned int* n_list, unsigned int* n_radau,
+                                      int sm_count, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(n_list, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const int tpb = 256;
+    radau_collect_kernel<<<(unsigned)((a.ns + tpb - 1) / tpb), tpb, 0, stream>>>(a.status, a.ns, list, n_list);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    RadauArgs ra;
+    ra.w = a;
+    ra.list = list;
+    ra.n_list = n_list;
+    ra.n_radau = n_radau;
+    // the list length lives on the device: a fixed grid strides over it (flagged links are rare)
+    const unsigned grid = (unsigned)std::min<long long>((a.ns + 63) / 64, (long long)sm_count * 4);
+    radau_window_kernel<Model><<<grid, 64, 0, stream>>>(ra);
+    return cudaGetLastError();
+}
+
+cudaError_t radau_launch(int uid, const WindowArgs& a, int* list, unsigned int* n_list, unsigned int* n_radau,
+                         int sm_count, cudaStream_t stream) {
+    if (uid == Model204::UID) return radau_launch_model<Model204>(a, list, n_list, n_radau, sm_count, stream);
+    if (uid == DummyModel::UID) return radau_launch_model<DummyModel>(a, list, n_list, n_radau, sm_count, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace hlm

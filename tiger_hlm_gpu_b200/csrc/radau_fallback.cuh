@@ -217,7 +217,7 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
                 lu_solve<N>(Mr, pivr, e);
                 err = err_norm(e);
             }
-            double fac = a.prm.safety * ::pow(1.0 / (err + 1e-16), 0.25);
+            double fac = a.prm.safety * sqrt(sqrt(1.0 / (err + 1e-16)));  // err^(-1/4) from IEEE operations only
             if (!(err == err)) { err = 2.0; fac = a.prm.minScale; }  // non-finite stage: treat as rejected
 
             if (err <= 1.0) {
