@@ -42,6 +42,11 @@ typedef enum hlm_status {
  * reference never assigned a UID. */
 #define HLM_MODEL_DUMMY 0
 #define HLM_MODEL_204 204
+/* 200 = hillslope-link runoff (channel discharge + Model204's hillslope stores without snow).  The
+ * reference names "model 200" (README.md:95) but ships no definition: this one is project-defined
+ * (csrc/models.cuh), pinned by its own CPU restatement and SciPy only.  It is the routed model: its
+ * channel takes the discharge of upstream links (hlm_route_*). */
+#define HLM_MODEL_200 200
 
 /* per-link result codes written to out_stiff: 0 = integrated to tf; 1 = flagged stiff and
  * abandoned, exactly the reference's d_stiff[sys] = 1 (solver/rk45_kernel.cu:160-170);
@@ -157,6 +162,11 @@ int hlm_solve_begin(hlm_ctx* ctx, int uid, const double* y0, long long ns, doubl
  * threshold h < (tf - t0) * 1e-6 (solver/rk45_kernel.cu:160) scales with the interval, so a
  * one-year interval would flag nearly every link, SURVEY §7.3. */
 int hlm_solve_restart(hlm_ctx* ctx, double t0, double tf, const double* tq, long long nq);
+/* Continue the session from its current end to a later tf with new query times: unlike hlm_solve_restart
+ * every link keeps its time and its step size (no ramp-up from initialStep), as if the previous interval
+ * had simply gone on.  The stiffness floor h < (tf - t0)*1e-6 (solver/rk45_kernel.cu:160) is taken over
+ * the new interval.  Used by routed runs, whose coupling intervals are short. */
+int hlm_solve_advance(hlm_ctx* ctx, double tf, const double* tq, long long nq);
 /* Advance every unfinished link until it has emitted all queries with index < q_hi (to tf when
  * q_hi >= nq).  Dense records of queries [previous q_hi, q_hi) go to a device buffer
  * [ns][q_hi - q_lo][N_EQ] owned by the context (skipped when want_dense == 0).  Asynchronous. */
@@ -192,6 +202,39 @@ long long hlm_launch_count(hlm_ctx* ctx);
 /* CUDA-event time, in ms, of the window kernels launched since the last call (sum), and how many.
  * Synchronises the context's stream. */
 int hlm_kernel_time_ms(hlm_ctx* ctx, double* sum_ms, long long* n_launches);
+
+/* ---- routed runs: links coupled through upstream channel discharge ----------------------------
+ *
+ * The reference carries `next_stream` in every parameter record (I_O/parameters_loader.cpp:74,
+ * stream.hpp:31,47) and sketches per-step MPI buffers (data/config.yaml:66-70) but couples nothing.
+ * Here a routed run advances in coupling intervals (hlm_solve_restart per interval): over an interval every
+ * link is integrated on its own with the discharge entering from upstream held at its value at the
+ * interval's start, so the RK45 path stays one independent system per thread; between intervals the
+ * inflow is re-gathered.  Across ranks only the discharge of boundary links (links whose downstream
+ * link another rank owns) is exchanged: the window kernel's epilogue writes it into the send buffer,
+ * the caller runs its collective (NCCL all-gather; MPI in the reference's world) on the same stream and
+ * hands the gathered halo vector to hlm_route_gather.
+ *
+ * Topology is CSR over the links this context owns, in the order of hlm_solve_begin's y0: the upstream
+ * links of link i are up_idx[up_ptr[i] .. up_ptr[i+1]).  An entry e >= 0 is a local link; e < 0 is
+ * element -(e+1) of the halo vector.  Entries are added in the order given (give them by ascending
+ * global link id and the sums are the same under every partition).  send_idx[n_send] lists the local
+ * links other ranks need, in the order of this rank's segment of the halo vector.  Copies its inputs. */
+int hlm_route_set_topology(hlm_ctx* ctx, const long long* up_ptr, const int* up_idx, long long ns,
+                           const int* send_idx, long long n_send);
+int hlm_route_clear(hlm_ctx* ctx);
+/* Where boundary discharge is written: NULL = a buffer of the context's own, else a device buffer of the
+ * caller's (n_send doubles, e.g. the input of its all-gather). */
+int hlm_route_set_send_buffer(hlm_ctx* ctx, double* dev_buf);
+int hlm_route_send_buffer(hlm_ctx* ctx, void** dev_ptr, long long* n_send);
+/* Fill the send buffer from the resident state.  Needed before the first interval only: afterwards the
+ * window kernel has already done it. */
+int hlm_route_pack(hlm_ctx* ctx);
+/* inflow[i] = sum of upstream discharge for the next interval; dev_halo (device pointer) may be NULL
+ * when no entry of up_idx is negative.  Queued on the context's stream. */
+int hlm_route_gather(hlm_ctx* ctx, const double* dev_halo);
+/* Download the current inflow [ns] and send buffer [n_send] (either may be NULL).  Synchronises. */
+int hlm_route_peek(hlm_ctx* ctx, double* out_qin, double* out_send);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 

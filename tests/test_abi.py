@@ -34,8 +34,9 @@ def test_abi_version_and_model_registry():
     assert lib.hlm_abi_version() == hlm.ABI_VERSION
     assert hlm.model_info(204) == (5, 15, 2)   # Model204::N_EQ = 5 (models/model_204.hpp:19)
     assert hlm.model_info(0) == (5, 0, 0)
+    assert hlm.model_info(200) == (5, 15, 2)   # project-defined hillslope-link model (README.md:95 names it only)
     with pytest.raises(hlm.HlmError, match="unknown model uid"):
-        hlm.model_info(200)
+        hlm.model_info(190)
 
 
 def test_reference_trait_constants():

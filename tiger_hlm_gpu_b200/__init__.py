@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     ABI_VERSION,
     DummyModel,
     HlmError,
+    Model200,
     Model204,
     Parameters,
     SPATIAL_PARAMS_DTYPE,
@@ -22,6 +23,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "ABI_VERSION", "DummyModel", "HlmError", "Model204", "Parameters", "SPATIAL_PARAMS_DTYPE", "Solver",
+    "ABI_VERSION", "DummyModel", "HlmError", "Model200", "Model204", "Parameters", "SPATIAL_PARAMS_DTYPE", "Solver",
     "lib_path", "load_library", "model_info", "run_rk45", "setModelParameters",
 ]

@@ -15,7 +15,7 @@ from dataclasses import dataclass, astuple
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -56,6 +56,7 @@ SIGNATURES = {
     "hlm_run_rk45": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL, _V, _V, _V, _V, _V, _V]),
     "hlm_solve_begin": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL]),
     "hlm_solve_restart": (_I, [_V, _D, _D, _V, _LL]),
+    "hlm_solve_advance": (_I, [_V, _D, _V, _LL]),
     "hlm_solve_window": (_I, [_V, _LL, _I]),
     "hlm_solve_window_buffer": (_I, [_V, C.POINTER(_V), C.POINTER(_LL), C.POINTER(_LL)]),
     "hlm_solve_fetch_window": (_I, [_V, _V]),
@@ -66,6 +67,13 @@ SIGNATURES = {
     "hlm_solve_totals": (_I, [_V, _V]),
     "hlm_solve_end": (_I, [_V, _V, _V, _V, _V, _V]),
     "hlm_solve_peek": (_I, [_V, _V, _V, _V]),
+    "hlm_route_set_topology": (_I, [_V, _V, _V, _LL, _V, _LL]),
+    "hlm_route_clear": (_I, [_V]),
+    "hlm_route_set_send_buffer": (_I, [_V, _V]),
+    "hlm_route_send_buffer": (_I, [_V, C.POINTER(_V), C.POINTER(_LL)]),
+    "hlm_route_pack": (_I, [_V]),
+    "hlm_route_gather": (_I, [_V, _V]),
+    "hlm_route_peek": (_I, [_V, _V, _V]),
     "hlm_launch_count": (_LL, [_V]),
     "hlm_kernel_time_ms": (_I, [_V, C.POINTER(_D), C.POINTER(_LL)]),
     "hlm_measure_fma_peak": (_I, [_V, _I, C.POINTER(_D)]),
@@ -122,6 +130,14 @@ class Parameters:
 
 class Model204:
     UID = 204
+    N_EQ = 5
+    SP_TYPE = SPATIAL_PARAMS_DTYPE
+    Parameters = Parameters
+
+
+class Model200:
+    """Hillslope-link runoff (project-defined; the reference names it, README.md:95, without defining it)."""
+    UID = 200
     N_EQ = 5
     SP_TYPE = SPATIAL_PARAMS_DTYPE
     Parameters = Parameters
@@ -265,6 +281,42 @@ class Solver:
         self._session = (uid, n_eq, ns, tq.shape[0])
         _check(self._lib.hlm_solve_restart(self._h, t0, tf, _p(tq), tq.shape[0]))
         self._keep.append(tq)
+
+    def solve_advance(self, tf: float, tq):
+        """Continue to a later tf keeping every link's time and step size (hlm_solve_advance)."""
+        tq = np.ascontiguousarray(tq if tq is not None else [], dtype=np.float64)
+        uid, n_eq, ns, _ = self._session
+        self._session = (uid, n_eq, ns, tq.shape[0])
+        _check(self._lib.hlm_solve_advance(self._h, tf, _p(tq), tq.shape[0]))
+        self._keep.append(tq)
+
+    # -- routed runs ---------------------------------------------------------------------------------
+    def route_set_topology(self, up_ptr, up_idx, send_idx=None):
+        up_ptr = np.ascontiguousarray(up_ptr, dtype=np.int64)
+        up_idx = np.ascontiguousarray(up_idx, dtype=np.int32)
+        send_idx = np.ascontiguousarray(send_idx if send_idx is not None else [], dtype=np.int32)
+        _check(self._lib.hlm_route_set_topology(self._h, _p(up_ptr), _p(up_idx) if up_idx.size else None,
+                                                up_ptr.shape[0] - 1, _p(send_idx) if send_idx.size else None,
+                                                send_idx.shape[0]))
+        self._route = (up_ptr.shape[0] - 1, send_idx.shape[0])
+
+    def route_clear(self):
+        _check(self._lib.hlm_route_clear(self._h))
+
+    def route_set_send_buffer(self, dev_ptr: int | None):
+        _check(self._lib.hlm_route_set_send_buffer(self._h, _V(dev_ptr) if dev_ptr else None))
+
+    def route_pack(self):
+        _check(self._lib.hlm_route_pack(self._h))
+
+    def route_gather(self, dev_halo: int | None = None):
+        _check(self._lib.hlm_route_gather(self._h, _V(dev_halo) if dev_halo else None))
+
+    def route_peek(self):
+        ns, n_send = self._route
+        qin, send = np.zeros(ns), np.zeros(n_send)
+        _check(self._lib.hlm_route_peek(self._h, _p(qin), _p(send) if n_send else None))
+        return qin, send
 
     def solve_window(self, q_hi: int, want_dense: bool = True):
         _check(self._lib.hlm_solve_window(self._h, q_hi, 1 if want_dense else 0))

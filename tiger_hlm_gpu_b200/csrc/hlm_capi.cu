@@ -73,6 +73,7 @@ struct ModelInfo {
 const ModelInfo kModels[] = {
     {hlm::DummyModel::UID, hlm::DummyModel::N_EQ, hlm::DummyModel::N_SP, hlm::DummyModel::N_FORC},
     {hlm::Model204::UID, hlm::Model204::N_EQ, hlm::Model204::N_SP, hlm::Model204::N_FORC},
+    {hlm::Model200::UID, hlm::Model200::N_EQ, hlm::Model200::N_SP, hlm::Model200::N_FORC},
 };
 const ModelInfo* find_model(int uid) {
     for (const auto& m : kModels)
@@ -135,6 +136,14 @@ struct hlm_ctx {
     DevBuf<int> radau_list;
     DevBuf<unsigned int> radau_count, n_radau;
 
+    // routed runs (models with upstream inflow): topology of the links this context owns
+    bool routed = false;
+    long long route_ns = 0, route_nnz = 0, route_n_send = 0;
+    DevBuf<long long> up_ptr;
+    DevBuf<int> up_idx, send_idx, send_slot;
+    DevBuf<double> qin, own_send;
+    double* send_buf = nullptr;  // own_send.p or the caller's (a buffer its collective reads)
+
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // per window kernel
     std::vector<cudaEvent_t> event_pool;
@@ -186,13 +195,16 @@ __global__ void init_state_kernel(const double* __restrict__ y0_aos, int n_eq, l
 
 // new interval from the resident final states: what a second run_rk45 call with y0 = previous
 // final does, without the host round trip.  Links that did not finish stay flagged.
+// keep_step: the interval continues the previous one (hlm_solve_advance) — time and step size stay.
 __global__ void restart_state_kernel(long long ld, double* __restrict__ t, double* __restrict__ h, int* next_q,
-                                     int* reject_run, int* status, double t0, double h0) {
+                                     int* reject_run, int* status, double t0, double h0, bool keep_step) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ld) return;
     if (status[i] == hlm::kDone || status[i] == hlm::kActive || status[i] == hlm::kDoneStiff) {
-        t[i] = t0;
-        h[i] = h0;
+        if (!keep_step) {
+            t[i] = t0;
+            h[i] = h0;
+        }
         next_q[i] = 0;
         reject_run[i] = 0;
         status[i] = hlm::kActive;
@@ -267,6 +279,28 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
     out[i] = r;
 }
 
+// ---- routing: boundary pack and upstream gather (HBM-bound plumbing around the window kernel) ----
+__global__ void route_pack_kernel(const double* __restrict__ q, const int* __restrict__ send_idx, long long n_send,
+                                  double* __restrict__ send_buf) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_send) send_buf[k] = q[send_idx[k]];
+}
+
+// qin[i] = sum of the discharge of link i's upstream links, added in the order the topology lists them
+// (ascending global link id), so the sum does not depend on how links are partitioned over ranks.
+__global__ void route_gather_kernel(const double* __restrict__ q, const double* __restrict__ halo,
+                                    const long long* __restrict__ up_ptr, const int* __restrict__ up_idx, long long ns,
+                                    double* __restrict__ qin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    double acc = 0.0;
+    for (long long e = up_ptr[i]; e < up_ptr[i + 1]; ++e) {
+        const int u = up_idx[e];
+        acc = __dadd_rn(acc, u >= 0 ? q[u] : halo[-(u + 1)]);
+    }
+    qin[i] = acc;
+}
+
 template <class Model> int prepare_params(hlm_ctx* c) {
     const long long ld = c->ld;
     if (Model::N_SP == 0) return 0;
@@ -318,6 +352,8 @@ template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::Wind
 int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     if (c->uid == hlm::Model204::UID)
         return c->precision == 32 ? launch_window<hlm::Model204, float>(c, a) : launch_window<hlm::Model204, double>(c, a);
+    if (c->uid == hlm::Model200::UID)
+        return c->precision == 32 ? launch_window<hlm::Model200, float>(c, a) : launch_window<hlm::Model200, double>(c, a);
     if (c->uid == hlm::DummyModel::UID)
         return c->precision == 32 ? launch_window<hlm::DummyModel, float>(c, a)
                                   : launch_window<hlm::DummyModel, double>(c, a);
@@ -336,7 +372,7 @@ int dispatch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
 // =================================================================================================
 extern "C" {
 
-int hlm_abi_version(void) { return 2; }
+int hlm_abi_version(void) { return 3; }
 
 const char* hlm_last_error(void) { return g_err.c_str(); }
 
@@ -599,12 +635,26 @@ int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double 
     ++c->launches;
     int r = 0;
     if (uid == hlm::Model204::UID) r = prepare_params<hlm::Model204>(c);
+    if (uid == hlm::Model200::UID) r = prepare_params<hlm::Model200>(c);
     if (r) return r;
     c->in_session = true;
     return HLM_OK;
 }
 
+static int restart_impl(hlm_ctx* c, double t0, double tf, const double* tq, long long nq, bool keep_step);
+
 int hlm_solve_restart(hlm_ctx* c, double t0, double tf, const double* tq, long long nq) {
+    return restart_impl(c, t0, tf, tq, nq, false);
+}
+
+int hlm_solve_advance(hlm_ctx* c, double tf, const double* tq, long long nq) {
+    HLM_REQUIRE(c, "hlm_solve_advance: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_advance: no session (call hlm_solve_begin)");
+    HLM_REQUIRE(tf >= c->tf, "hlm_solve_advance: tf must not move backwards");
+    return restart_impl(c, c->tf, tf, tq, nq, true);
+}
+
+static int restart_impl(hlm_ctx* c, double t0, double tf, const double* tq, long long nq, bool keep_step) {
     HLM_REQUIRE(c, "hlm_solve_restart: ctx is NULL");
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_restart: no session (call hlm_solve_begin)");
     HLM_REQUIRE(nq >= 0 && nq < (1LL << 31) && (nq == 0 || tq), "hlm_solve_restart: bad query times");
@@ -615,7 +665,7 @@ int hlm_solve_restart(hlm_ctx* c, double t0, double tf, const double* tq, long l
     // padding lanes beyond ns carry status kDone from init and are re-armed here; the window kernel
     // never touches them (sys >= ns), so that is harmless
     restart_state_kernel<<<(unsigned)((c->ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
-        c->ld, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p, t0, c->params[c->uid].initialStep);
+        c->ld, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p, t0, c->params[c->uid].initialStep, keep_step);
     HLM_CUDA(cudaGetLastError());
     ++c->launches;
     c->t0 = t0;
@@ -687,6 +737,12 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     a.ns = c->ns; a.ld = c->ld;
     a.max_attempts = c->max_attempts;
     a.tile_counter = c->tile_counter.p;
+    if (c->routed) {
+        if (c->route_ns != c->ns) return fail(HLM_ERR_STATE, "hlm_solve_window: routing topology was set for another link count");
+        a.qin = c->qin.p;
+        a.send_slot = c->route_n_send > 0 ? c->send_slot.p : nullptr;
+        a.send_buf = c->send_buf;
+    }
     if (int r = dispatch_window(c, a)) return r;
     if (c->stiff_fallback)
         if (int r = dispatch_radau(c, a)) return r;
@@ -881,6 +937,108 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
         }
     }
     return hlm_solve_end(c, out_final, out_stiff, out_acc, out_rej, out_jump);
+}
+
+// ---- routed runs ---------------------------------------------------------------------------------
+
+int hlm_route_set_topology(hlm_ctx* c, const long long* up_ptr, const int* up_idx, long long ns, const int* send_idx,
+                           long long n_send) {
+    HLM_REQUIRE(c && up_ptr && ns > 0 && n_send >= 0, "hlm_route_set_topology: bad argument");
+    HLM_REQUIRE(up_ptr[0] == 0 && up_ptr[ns] >= 0 && (up_ptr[ns] == 0 || up_idx), "hlm_route_set_topology: bad CSR");
+    HLM_REQUIRE(n_send == 0 || send_idx, "hlm_route_set_topology: send_idx is NULL");
+    if (int r = use_device(c)) return r;
+    const long long nnz = up_ptr[ns];
+    const long long ld = (ns + 31) & ~31LL;
+    for (long long i = 0; i < ns; ++i)
+        if (up_ptr[i + 1] < up_ptr[i]) return fail(HLM_ERR_INVALID, "hlm_route_set_topology: up_ptr is not ascending");
+    for (long long e = 0; e < nnz; ++e)
+        if (up_idx[e] >= ns) return fail(HLM_ERR_INVALID, "hlm_route_set_topology: upstream index out of range");
+    std::vector<int> slot;
+    try { slot.assign((size_t)ld, -1); } catch (const std::bad_alloc&) { return fail(HLM_ERR_NOMEM, "hlm_route_set_topology: out of host memory"); }
+    for (long long k = 0; k < n_send; ++k) {
+        if (send_idx[k] < 0 || send_idx[k] >= ns) return fail(HLM_ERR_INVALID, "hlm_route_set_topology: send index out of range");
+        slot[(size_t)send_idx[k]] = (int)k;
+    }
+    HLM_CUDA(cudaStreamSynchronize(c->stream));  // kernels queued with the old topology
+    HLM_CUDA(c->up_ptr.reserve((size_t)ns + 1));
+    HLM_CUDA(c->up_idx.reserve((size_t)std::max<long long>(nnz, 1)));
+    HLM_CUDA(c->send_idx.reserve((size_t)std::max<long long>(n_send, 1)));
+    HLM_CUDA(c->send_slot.reserve((size_t)ld));
+    HLM_CUDA(c->own_send.reserve((size_t)std::max<long long>(n_send, 1)));
+    HLM_CUDA(c->qin.reserve((size_t)ld));
+    HLM_CUDA(cudaMemcpyAsync(c->up_ptr.p, up_ptr, sizeof(long long) * (size_t)(ns + 1), cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) HLM_CUDA(cudaMemcpyAsync(c->up_idx.p, up_idx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, c->stream));
+    if (n_send > 0) HLM_CUDA(cudaMemcpyAsync(c->send_idx.p, send_idx, sizeof(int) * (size_t)n_send, cudaMemcpyHostToDevice, c->stream));
+    HLM_CUDA(cudaMemcpyAsync(c->send_slot.p, slot.data(), sizeof(int) * (size_t)ld, cudaMemcpyHostToDevice, c->stream));
+    HLM_CUDA(cudaMemsetAsync(c->qin.p, 0, sizeof(double) * (size_t)ld, c->stream));
+    HLM_CUDA(cudaMemsetAsync(c->own_send.p, 0, sizeof(double) * (size_t)std::max<long long>(n_send, 1), c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));  // the host arrays (and `slot`) may go away after return
+    c->routed = true;
+    c->route_ns = ns;
+    c->route_nnz = nnz;
+    c->route_n_send = n_send;
+    c->send_buf = c->own_send.p;
+    return HLM_OK;
+}
+
+int hlm_route_clear(hlm_ctx* c) {
+    HLM_REQUIRE(c, "hlm_route_clear: ctx is NULL");
+    c->routed = false;
+    c->route_ns = c->route_nnz = c->route_n_send = 0;
+    c->send_buf = nullptr;
+    return HLM_OK;
+}
+
+int hlm_route_set_send_buffer(hlm_ctx* c, double* dev_buf) {
+    HLM_REQUIRE(c, "hlm_route_set_send_buffer: ctx is NULL");
+    if (!c->routed) return fail(HLM_ERR_STATE, "hlm_route_set_send_buffer: no topology");
+    c->send_buf = dev_buf ? dev_buf : c->own_send.p;
+    return HLM_OK;
+}
+
+int hlm_route_send_buffer(hlm_ctx* c, void** dev_ptr, long long* n_send) {
+    HLM_REQUIRE(c, "hlm_route_send_buffer: ctx is NULL");
+    if (!c->routed) return fail(HLM_ERR_STATE, "hlm_route_send_buffer: no topology");
+    if (dev_ptr) *dev_ptr = c->send_buf;
+    if (n_send) *n_send = c->route_n_send;
+    return HLM_OK;
+}
+
+int hlm_route_pack(hlm_ctx* c) {
+    HLM_REQUIRE(c, "hlm_route_pack: ctx is NULL");
+    if (!c->routed || !c->in_session) return fail(HLM_ERR_STATE, "hlm_route_pack: needs a topology and a session");
+    if (int r = use_device(c)) return r;
+    if (c->route_n_send == 0) return HLM_OK;
+    const int tpb = 256;
+    route_pack_kernel<<<(unsigned)((c->route_n_send + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, c->send_idx.p,
+                                                                                          c->route_n_send, c->send_buf);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    return HLM_OK;
+}
+
+int hlm_route_gather(hlm_ctx* c, const double* dev_halo) {
+    HLM_REQUIRE(c, "hlm_route_gather: ctx is NULL");
+    if (!c->routed || !c->in_session) return fail(HLM_ERR_STATE, "hlm_route_gather: needs a topology and a session");
+    if (c->route_ns != c->ns) return fail(HLM_ERR_STATE, "hlm_route_gather: topology was set for another link count");
+    if (int r = use_device(c)) return r;
+    const int tpb = 256;
+    route_gather_kernel<<<(unsigned)((c->ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, dev_halo, c->up_ptr.p,
+                                                                                   c->up_idx.p, c->ns, c->qin.p);
+    HLM_CUDA(cudaGetLastError());
+    ++c->launches;
+    return HLM_OK;
+}
+
+int hlm_route_peek(hlm_ctx* c, double* out_qin, double* out_send) {
+    HLM_REQUIRE(c, "hlm_route_peek: ctx is NULL");
+    if (!c->routed) return fail(HLM_ERR_STATE, "hlm_route_peek: no topology");
+    if (int r = use_device(c)) return r;
+    if (out_qin) HLM_CUDA(cudaMemcpyAsync(out_qin, c->qin.p, sizeof(double) * (size_t)c->route_ns, cudaMemcpyDeviceToHost, c->stream));
+    if (out_send && c->route_n_send > 0)
+        HLM_CUDA(cudaMemcpyAsync(out_send, c->send_buf, sizeof(double) * (size_t)c->route_n_send, cudaMemcpyDeviceToHost, c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    return HLM_OK;
 }
 
 int hlm_debug_eval(hlm_ctx* c, int op, const double* x, const double* y, double* out, long long n) {

@@ -37,6 +37,7 @@ struct Model204 {
     static constexpr int N_EQ = 5;
     static constexpr int N_SP = 15;
     static constexpr int N_FORC = 2;
+    static constexpr bool HAS_INFLOW = false;
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };  // R_* = fp<double>::div_recip of the divisor
 
@@ -132,6 +133,122 @@ struct Model204 {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Model 200 — hillslope-link runoff: channel discharge + static / surface / gravitational / aquifer
+// storages.  PROJECT-DEFINED, NOT REFERENCE-DERIVED: the reference only names "model 200/204"
+// (README.md:95) and ships no definition.  It is Model204's hillslope without the
+// snow store (same expressions, same two contractions) draining into the link's channel with the
+// Hillslope-Link Model's nonlinear-celerity routing equation (Mantilla & Gupta 2005; the form the
+// Iowa HLM uses):
+//     dq/dt = invtau * q_e^0.2 * ((runoff*CH + q_in) - q),   q_e = max(q, 1e-6 m3/s)
+//     runoff = (h_surf*w + out_grav) + out_aq   [m/min],  CH = A_h * 1e6/60  [km2 * m/min -> m3/s]
+//     invtau = 19.8 / ((800 * L) * sqrt(A_h^0.2))   [1/min]   (v_r 0.33 m/s, lambda1 0.2, lambda2 -0.1)
+// q_in is the discharge entering from upstream links (0 for an unrouted run); it is constant over an
+// interval, set per link through WindowArgs::qin (routing, rk45_window.cuh).  The CPU restatement the
+// tests compare with lives with the test infrastructure; the independent pin is SciPy (tests).
+// ---------------------------------------------------------------------------------------------
+struct Model200 {
+    static constexpr int UID = 200;
+    static constexpr int N_EQ = 5;
+    static constexpr int N_SP = 15;
+    static constexpr int N_FORC = 2;
+    static constexpr bool HAS_INFLOW = true;
+    enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, CH, INVTAU,
+           R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };
+
+    static __device__ __forceinline__ void prepare(const SpatialParamsAoS& s, double* out) {
+        out[INFIL] = s.infil;
+        out[PERCO] = s.perco;
+        out[HU] = s.Hu;
+        out[INV_N] = __drcp_rn(s.n_mann);
+        out[SQRT_SLOPE] = __dsqrt_rn(s.slope);
+        out[LEN] = s.L;
+        out[A_H] = s.A_h;
+        out[ALPHA3] = s.alpha3;
+        out[ALPHA4] = s.alpha4;
+        out[CH] = __dmul_rn(s.A_h, 1.0e6 / 60.0);
+        bool unused = false;
+        const double a02 = fp<double>::pow_pos<false>(s.A_h, 0.2, unused);
+        out[INVTAU] = __ddiv_rn(19.8, __dmul_rn(__dmul_rn(800.0, s.L), __dsqrt_rn(a02)));
+        out[R_HU] = fp<double>::div_recip(s.Hu);
+        out[R_A_H] = fp<double>::div_recip(s.A_h);
+        out[R_ALPHA3] = (s.alpha3 >= 1.0) ? fp<double>::div_recip(s.alpha3) : 0.0;
+        out[R_ALPHA4] = (s.alpha4 >= 1.0) ? fp<double>::div_recip(s.alpha4) : 0.0;
+    }
+
+    template <typename T> struct Link {
+        T p[N_SP];
+        T qin;
+        const double* wet;
+        long long ld;
+        bool recips_ok;
+        __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld_, long long sys) {
+            const int dry[] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, CH, INVTAU, R_HU, R_ALPHA3, R_ALPHA4};
+#pragma unroll
+            for (int i = 0; i < 10; ++i) p[dry[i]] = (T)__ldg(sp + (long long)dry[i] * ld_ + sys);
+            wet = sp + sys;
+            ld = ld_;
+            qin = (T)0;
+            const double ra = __ldg(sp + (long long)R_A_H * ld_ + sys);
+            recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
+        }
+        __device__ __forceinline__ void set_inflow(T v) { qin = v; }
+        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + (long long)c * ld); }
+    };
+
+    template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) { return P.recips_ok; }
+
+    template <typename T, bool kFast>
+    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, bool& bad) {
+        using f = fp<T>;
+        const T q = y[0], h_stat = y[1], h_surf = y[2], h_grav = y[3], h_aq = y[4];
+        const T rainfall = F[0], temperature = F[1];
+
+        // static store (Model204 without snow: x1 = rainfall)
+        const T x2 = f::max_a((T)0, f::sub(f::add(rainfall, h_stat), P.p[HU]));
+        const T d1 = f::sub(rainfall, x2);
+        const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
+        const T s = f::template div_by<kFast>(h_stat, P.p[HU], P.p[R_HU], bad);
+        dydt[1] = f::fma(-s, Emax, d1);
+
+        // surface store; its outflow h_surf*w feeds the channel
+        const T x3 = f::min_a(P.p[INFIL], x2);
+        const T d2 = f::sub(x2, x3);
+        T out_surf;
+        if (h_surf == (T)0) {
+            dydt[2] = d2;
+            out_surf = (T)0;
+        } else {
+            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::template pow_pos<kFast>(h_surf, (T)(2.0 / 3.0), bad)), P.wet_param(SQRT_SLOPE));
+            const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
+                                                                      P.wet_param(R_A_H), bad), (T)60));
+            dydt[2] = f::fma(-h_surf, w, d2);
+            out_surf = f::mul(h_surf, w);
+        }
+
+        // gravitational and aquifer stores
+        const T x4 = f::min_a(P.p[PERCO], x3);
+        const T d3 = f::sub(x3, x4);
+        T out_grav, out_aq;
+        if (kFast && sizeof(T) == 8) {
+            out_grav = f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad);
+            out_aq = f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad);
+        } else {
+            out_grav = (P.p[ALPHA3] >= (T)1) ? f::div(h_grav, P.p[ALPHA3]) : (T)0;
+            out_aq = (P.p[ALPHA4] >= (T)1) ? f::div(h_aq, P.p[ALPHA4]) : (T)0;
+        }
+        dydt[3] = f::sub(d3, out_grav);
+        dydt[4] = f::sub(x4, out_aq);
+
+        // channel
+        const T runoff = f::add(f::add(out_surf, out_grav), out_aq);
+        const T lateral = f::mul(runoff, P.p[CH]);
+        const T qe = f::max_a((T)1e-6, q);
+        const T cel = f::template pow_pos<kFast>(qe, (T)0.2, bad);
+        dydt[0] = f::mul(f::mul(P.p[INVTAU], cel), f::sub(f::add(lateral, P.qin), q));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // DummyModel — the 5-state linear test system of model_dummy_python.ipynb:65-89 (code cell,
 // I2 = 0.6*H1).  The reference ships no C++ for it; operations are unfused, in the
 // order Python evaluates the notebook's expressions, and match oracle/oracle_rk45.c:rhs_dummy.
@@ -142,6 +259,7 @@ struct DummyModel {
     static constexpr int N_EQ = 5;
     static constexpr int N_SP = 0;
     static constexpr int N_FORC = 0;
+    static constexpr bool HAS_INFLOW = false;
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS&, double*) {}
     template <typename T> struct Link {
         __device__ __forceinline__ void load(const double*, long long, long long) {}

@@ -30,6 +30,7 @@ static cudaError_t radau_launch_model(const WindowArgs& a, int* list, unsigned i
 cudaError_t radau_launch(int uid, const WindowArgs& a, int* list, unsigned int* n_list, unsigned int* n_radau,
                          int sm_count, cudaStream_t stream) {
     if (uid == Model204::UID) return radau_launch_model<Model204>(a, list, n_list, n_radau, sm_count, stream);
+    if (uid == Model200::UID) return radau_launch_model<Model200>(a, list, n_list, n_radau, sm_count, stream);
     if (uid == DummyModel::UID) return radau_launch_model<DummyModel>(a, list, n_list, n_radau, sm_count, stream);
     return cudaErrorInvalidValue;
 }

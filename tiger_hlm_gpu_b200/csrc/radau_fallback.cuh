@@ -106,6 +106,7 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
         unsigned int n_rej = a.n_reject[sys], n_imp = ra.n_radau[sys];
         typename Model::template Link<double> L;
         L.load(a.sp, a.ld, sys);
+        if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? __ldg(a.qin + sys) : 0.0);
         const long long col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
         // the RK45 path leaves h below its stiffness threshold; start from the configured initial step
         if (a.status[sys] == kStiff && (!(h > 0.0) || h < a.prm.initialStep)) h = a.prm.initialStep;
@@ -257,6 +258,12 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
         a.status[sys] = status;
         a.n_reject[sys] = n_rej;
         ra.n_radau[sys] = n_imp;
+        if constexpr (Model::HAS_INFLOW) {
+            if (a.send_slot != nullptr && status != kStiffPaused) {
+                const int slot = __ldg(a.send_slot + sys);
+                if (slot >= 0) a.send_buf[slot] = y[0];
+            }
+        }
     }
 }
 

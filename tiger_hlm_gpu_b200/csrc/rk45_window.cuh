@@ -151,6 +151,12 @@ struct WindowArgs {
     long long ns, ld;
     long long max_attempts;  // per link per launch; <=0 = unbounded like the reference
     unsigned int* tile_counter;
+    // routed models (Model::HAS_INFLOW): discharge entering each link from upstream, constant over the
+    // interval (nullptr = unrouted, 0); and, for links another rank needs, where the epilogue puts the
+    // link's discharge once the interval is integrated (send_slot[sys] < 0: not a boundary link)
+    const double* qin;     // [ld]
+    const int* send_slot;  // [ld] or nullptr
+    double* send_buf;
 };
 
 template <typename T, int N>
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         unsigned int n_acc = a.n_accept[sys], n_rej = a.n_reject[sys], n_jmp = a.n_jump[sys];
         typename Model::template Link<T> L;
         L.load(a.sp, a.ld, sys);
+        if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
         const bool fast_ok = Model::template fast_div_ok<T>(L);
         const long long col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
 
@@ -401,6 +408,14 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         a.n_accept[sys] = n_acc;
         a.n_reject[sys] = n_rej;
         a.n_jump[sys] = n_jmp;
+        // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
+        // links need for the next interval goes straight into the send buffer
+        if constexpr (Model::HAS_INFLOW) {
+            if (a.send_slot != nullptr && status != kActive) {
+                const int slot = __ldg(a.send_slot + sys);
+                if (slot >= 0) a.send_buf[slot] = (double)y[0];
+            }
+        }
     }
 }
 

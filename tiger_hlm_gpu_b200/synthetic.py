@@ -82,3 +82,33 @@ def hourly_queries(t0: float, tf: float) -> np.ndarray:
 def expand_forcing_per_link(grid: np.ndarray, col: np.ndarray) -> np.ndarray:
     """The reference's per-link expansion [time][system] (main.cpp:543-548) of a grid forcing."""
     return np.ascontiguousarray(grid[:, col])
+
+
+Y0_200 = (0.5, 3.0, 0.0, 5.0, 0.2)  # channel discharge 0.5 m3/s + Model204's hillslope stores (main.cpp:376)
+
+
+def make_network(ns: int, subbasin_links: int = 4096, seed: int = 200) -> np.ndarray:
+    """Downstream link index per link (-1 = outlet) of a synthetic river network ("parent in a
+    random binary-ish tree per sub-basin of 4096 links").
+
+    Links come in consecutive groups of `subbasin_links`; inside a group link j > 0 drains into the link
+    before it (main stem, half of the time) or into a random earlier link at most 64 back (a tributary
+    joining), and the group's first link drains into a random link of one of the 8 groups before it, so the
+    groups themselves form a tree whose edges are what a partition by sub-basin cuts."""
+    rng = np.random.default_rng(seed)
+    j = np.arange(ns, dtype=np.int64) % subbasin_links
+    g0 = np.arange(ns, dtype=np.int64) - j                     # first link of the group
+    back = np.where(rng.random(ns) < 0.5, 1, rng.integers(1, 65, ns))
+    down = g0 + np.maximum(j - back, 0)
+    heads = np.flatnonzero(j == 0)
+    for h in heads:                                            # one entry per group: cheap
+        lo = max(0, h - 8 * subbasin_links)
+        down[h] = -1 if h == 0 else rng.integers(lo, h)
+    return down
+
+
+def apply_network(sp: np.ndarray, down: np.ndarray) -> np.ndarray:
+    """Write the topology into the records the way the reference's CSV carries it (stream, next_stream)."""
+    sp = sp.copy()
+    sp["next_stream"] = np.where(down >= 0, sp["stream"][np.maximum(down, 0)], 0)
+    return sp
