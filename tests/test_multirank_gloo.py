@@ -62,3 +62,55 @@ def test_two_gloo_ranks_reproduce_the_unsharded_run(tmp_path):
     for p in parts:
         assert float(p["ms"]) == 11.0                       # MAX over ranks
         assert p["sums"].tolist() == [float(whole["n_accept"].sum()), float(ns)]  # SUM over ranks
+
+
+# ---- routed runs: partition by sub-basin, boundary links exchanged with one all-gather per interval ----
+
+def _routed_case(ns=120, seed=5):
+    from tests.test_oracle_model200 import network_case
+    sp, down, rain, temp, pr, t2m, y0 = network_case(ns=ns, seed=seed)
+    return sp, pr, t2m, y0
+
+
+def _routed_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from tests import routed_ref
+    from tiger_hlm_gpu_b200 import routing
+    sp, pr, t2m, y0 = _routed_case()
+    p = routing.plan(sp["stream"], sp["next_stream"], world, subbasin_links=10)
+    topo = p.ranks[rank]
+    sel = p.order[topo.lo:topo.hi]
+    rk = routed_ref.OracleRank(topo, sp[sel], O.Forcing([pr[:, sel], t2m[:, sel]], [1.0, 24.0]), y0[sel],
+                               O.Params.make(initialStep=1e-6), 0.0, threads=1)
+    halo = torch.zeros(p.halo_len, dtype=torch.float64)
+    for b in np.arange(15.0, 120.0 + 1e-9, 15.0):
+        dist.all_gather_into_tensor(halo, torch.from_numpy(rk.send(p.max_send)))   # the exchange of RoutedSolver
+        rk.gather(halo.numpy())
+        rk.advance(b, np.array([b]))
+    np.savez(os.path.join(out_dir, f"routed{rank}.npz"), final=rk.y, n_accept=rk.na, sel=sel, cut=p.n_cut_edges)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_reproduce_the_single_rank_routed_run(tmp_path):
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_routed_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from oracle import oracle as O
+    from tests import routed_ref
+    from tiger_hlm_gpu_b200 import routing
+    sp, pr, t2m, y0 = _routed_case()
+    p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=10)
+    fin, _, _, na = routed_ref.run_single(sp, O.Forcing([pr, t2m], [1.0, 24.0]), y0, O.Params.make(initialStep=1e-6), p1,
+                                          0.0, 120.0, 15.0, threads=1)
+    parts = [np.load(tmp_path / f"routed{r}.npz") for r in range(world)]
+    assert int(parts[0]["cut"]) > 0                       # the partition really cuts the network
+    got_fin, got_na = np.zeros_like(fin), np.zeros_like(na)
+    for q in parts:
+        got_fin[q["sel"]], got_na[q["sel"]] = q["final"], q["n_accept"]
+    assert np.array_equal(got_fin, fin) and np.array_equal(got_na, na)

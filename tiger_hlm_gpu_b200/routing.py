@@ -205,26 +205,33 @@ class RoutedSolver:
     solver: a tiger_hlm_gpu_b200.Solver with parameters/forcings uploaded for this rank's links (planned
     order).  dist: torch.distributed (NCCL) or None for a single rank.  Everything — window kernel (which
     packs the boundary discharge in its epilogue), all-gather, inflow gather — is queued on torch's current
-    stream; nothing synchronises with the host between intervals."""
+    stream; nothing synchronises with the host between intervals.  The implicit fallback is switched on for
+    the run: a link the explicit path abandons would otherwise freeze and starve everything downstream."""
 
     def __init__(self, solver, uid: int, topo: RankTopology, world: int, max_send: int, dist=None, device=None):
         import torch
         self.torch = torch
         self.s, self.uid, self.topo, self.world, self.max_send, self.dist = solver, uid, topo, world, max_send, dist
         self.device = device if device is not None else torch.device("cuda", solver.device)
-        solver.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # a stream of its own (torch's default stream has handle 0, which hlm_set_stream reads as "the
+        # context's own stream"): kernels and collectives are ordered by it, never by the host
+        self.stream = torch.cuda.Stream(self.device)
+        solver.set_stream(self.stream.cuda_stream)
         solver.route_set_topology(topo.up_ptr, topo.up_idx, topo.send_idx)
+        solver.set_stiff_fallback(True)
         self.send = self.halo = None
         if world > 1 and max_send > 0:
-            self.send = torch.zeros(max_send, dtype=torch.float64, device=self.device)
-            self.halo = torch.zeros(world * max_send, dtype=torch.float64, device=self.device)
+            with torch.cuda.stream(self.stream):
+                self.send = torch.zeros(max_send, dtype=torch.float64, device=self.device)
+                self.halo = torch.zeros(world * max_send, dtype=torch.float64, device=self.device)
             solver.route_set_send_buffer(self.send.data_ptr())
         self._started = False
         self.exchanges = 0
 
     def _exchange_and_gather(self):
         if self.halo is not None:
-            self.dist.all_gather_into_tensor(self.halo, self.send)
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_gather_into_tensor(self.halo, self.send)
             self.exchanges += 1
             self.s.route_gather(self.halo.data_ptr())
         else:
@@ -249,4 +256,5 @@ class RoutedSolver:
     def end(self):
         r = self.s.solve_end()
         self.s.set_stream(None)
+        self.s.set_stiff_fallback(False)
         return r

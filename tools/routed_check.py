@@ -47,7 +47,13 @@ def main():
         p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=sub)
         F = O.Forcing([pr, t2m], [1.0, 24.0], col=col)
         fin_o, _, _, na_o = routed_ref.run_single(sp, F, y0, OPRM, p1, 0.0, tf, dt, threads=os.cpu_count() or 4)
-        assert np.array_equal(na.cpu().numpy().astype(np.int64), na_o), "accepted-step counts differ"
+        na_g = na.cpu().numpy().astype(np.int64)
+        if not np.array_equal(na_g, na_o):
+            bad = np.flatnonzero(na_g != na_o)
+            inv = p.inverse_order()
+            print("mismatching links", bad.size, bad[:10], "planned pos", inv[bad[:10]], "ranges", p.ranges,
+                  "gpu", na_g[bad[:10]], "oracle", na_o[bad[:10]], "stiff codes", np.unique(r["stiff"], return_counts=True))
+        assert np.array_equal(na_g, na_o), "accepted-step counts differ"
         assert np.array_equal(fin.cpu().numpy(), fin_o), "final states differ"
         print(f"routed_check ok: world {world}, {ns} links, {p.n_subbasins} sub-basins, {p.n_cut_edges} cut edges, "
               f"{rs.exchanges} all-gathers of {p.halo_len} doubles, bit-identical to the single-rank CPU oracle")
