@@ -50,7 +50,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--links-per-gpu", type=int, default=10_000_000)
+    ap.add_argument("--workload", default="model204", choices=["model204", "routed"],
+                    help="model204 = BASELINE configs[3] (the headline); routed = configs[4]: Model 200 links coupled "
+                         "through upstream discharge, partitioned by sub-basin, boundary links exchanged over NCCL")
+    ap.add_argument("--links-per-gpu", type=int, default=None, help="default 10M (model204) / 2.5M (routed)")
+    ap.add_argument("--couple-minutes", type=float, default=15.0, help="routed: coupling interval")
     ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
     ap.add_argument("--wet-fraction", type=float, default=0.0,
                     help="share of links started with surface storage so Model204's pow() branch runs")
@@ -210,6 +214,155 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+W_MIN_FLOP_PER_ATTEMPT_200 = 585.0  # as W_min with Model 200's rhs (36 nominal flop instead of 32), DESIGN.md
+
+
+def run_routed_arm(args):
+    """BASELINE configs[4]: Model 200 on a synthetic river network, partitioned by sub-basin over the ranks,
+    boundary discharge exchanged with one NCCL all-gather per coupling interval.  One step = one simulated
+    hour (60 / couple_minutes intervals).  Weak scaling: links_per_gpu links per rank."""
+    import torch
+    import tiger_hlm_gpu_b200 as hlm
+    from tiger_hlm_gpu_b200 import routing, synthetic
+    from tiger_hlm_gpu_b200.sharding import reduce_timing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    ns_all = args.links_per_gpu * world
+    dt = args.couple_minutes
+    n_int = max(1, int(round(60.0 / dt)))
+    days = max(2, (W + 2 * K + 24) // 24 + 1)
+    # every rank builds the same network and plan (seeded), then keeps its own part
+    sp_all = synthetic.apply_network(synthetic.make_spatial_params(ns_all), synthetic.make_network(ns_all))
+    plan = routing.plan(sp_all["stream"], sp_all["next_stream"], world)
+    topo = plan.ranks[rank]
+    sel = plan.order[topo.lo:topo.hi]
+    col_all, ncells = synthetic.make_cells(ns_all)
+    pr, t2m = synthetic.make_forcing_grid(ncells, days)
+    rng = np.random.default_rng(7)
+    y0 = np.tile(np.array(synthetic.Y0_200), (sel.size, 1))
+    y0[:, 0] = rng.uniform(0.05, 5.0, ns_all)[sel]
+    solver = hlm.Solver(local_rank)
+    solver.set_model_parameters(200, hlm.Parameters(*PRM6))
+    solver.set_max_attempts(5_000_000)
+    solver.upload_spatial_params(sp_all[sel])
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(col_all[sel])
+    del sp_all
+    fp_peak = solver.measure_fma_peak(64)
+    rs = routing.RoutedSolver(solver, 200, topo, world, plan.max_send, dist)
+    stream = rs.stream
+
+    def hour(k, first=False):
+        for i in range(n_int):
+            tf = 60.0 * k + dt * (i + 1)
+            tq = np.array([tf])
+            if first and i == 0:
+                rs.begin(y0, 0.0, tf, tq)
+            rs.advance(tf, tq)
+
+    for k in range(W):
+        hour(k, first=(k == 0))
+    solver.synchronize()
+    tot0 = solver.solve_totals()
+    solver.kernel_time_ms()
+    launches0 = solver.launch_count()
+    ex0 = rs.exchanges
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(W, W + K):
+        hour(k, first=(k == 0))
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = solver.kernel_time_ms()
+    launches = solver.launch_count() - launches0
+    tot1 = solver.solve_totals()
+    radau = int(solver.solve_radau_steps().sum())
+    acc = tot1["n_accept"] - tot0["n_accept"]
+    attempts = acc + (tot1["n_reject"] - tot0["n_reject"]) + (tot1["n_jump"] - tot0["n_jump"])
+    state = dict(tot1)
+
+    # e2e: the same intervals, with the host in the loop as a caller writing hourly output has it: the hour's
+    # last dense record (discharge + stores of every link) is copied to pinned host memory every step, and the
+    # first step uploads y0.  (Between intervals nothing else crosses PCIe: state stays resident.)
+    e2e = None
+    if not args.no_e2e:
+        win = torch.zeros((sel.size, 1, 5), dtype=torch.float64).pin_memory()
+        barrier()
+        t_start = time.perf_counter()
+        acc_before = solver.solve_totals()["n_accept"]
+        for k in range(W + K, W + 2 * K):
+            hour(k)
+            solver.solve_wait_copy(solver.solve_fetch_window_packed(win.numpy()))
+        barrier()
+        e_ms = (time.perf_counter() - t_start) * 1e3
+        acc_e = solver.solve_totals()["n_accept"] - acc_before
+        e_ms_max, (acc_e_all,) = reduce_timing(e_ms, [acc_e], dist, dev)
+        e2e = {"value": acc_e_all / (e_ms_max * 1e-3), "unit": "accepted system-steps/s", "h2d_bytes_per_step": 8 * n_int,
+               "d2h_bytes_per_step": int(sel.size) * 40 + 56, "ms_per_step": e_ms_max / K,
+               "api": "routing.RoutedSolver over the C ABI (hlm_route_gather + hlm_solve_advance + hlm_solve_window + "
+                      "hlm_solve_fetch_window_packed), pinned host buffer; state resident between intervals"}
+    rs.end()
+
+    ms_max, (acc_all, att_all, launches_all, kern_ms_all, kern_n_all, radau_all) = reduce_timing(
+        ms, [acc, attempts, launches, kern_ms, kern_n, radau], dist, dev)
+    if rank == 0:
+        kern_avg_ms = kern_ms_all / max(kern_n_all, 1)
+        att_per_launch = att_all / max(kern_n_all, 1)
+        achieved = W_MIN_FLOP_PER_ATTEMPT_200 * att_per_launch / (kern_avg_ms * 1e-3) / 1e12
+        line = {
+            "metric": "accepted RK45 system-steps/sec", "value": acc_all / (ms_max * 1e-3), "unit": "accepted system-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "routed sub-basin network (BASELINE configs[4]): Model 200 (project-defined), synthetic "
+                                   "river network, links coupled through upstream discharge held over a coupling interval; "
+                                   "one step = one simulated hour",
+                       "links_per_gpu": args.links_per_gpu, "links_total": ns_all, "couple_minutes": dt,
+                       "intervals_per_step": n_int, "sub_basins": plan.n_subbasins, "cut_edges": plan.n_cut_edges,
+                       "halo_doubles": plan.halo_len, "rtol": PRM6[1], "atol": PRM6[2],
+                       "parallelism": f"sub-basins dealt to {world} GPU(s); one NCCL all-gather of the boundary vector per interval"
+                                      if world > 1 else "1 GPU, no exchange",
+                       "l2": "inputs larger than L2 (state + parameters of the rank's links >> 126 MB)"},
+            "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),
+            "implicit_steps_total": radau_all, "exchanges_per_step": (rs.exchanges - ex0) / max(1, 2 * K if e2e else K),
+            "link_status_after_run": {k: state[k] for k in ("active", "done", "stiff", "stalled")},
+            "e2e": e2e, "gpu_launches": int(launches_all),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp_peak, "unit": "TFLOP/s", "frac": achieved / fp_peak,
+                         "traffic": None, "flop_per_attempt": W_MIN_FLOP_PER_ATTEMPT_200, "attempts_per_launch": att_per_launch,
+                         "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_window_kernel<Model200,double>",
+                         "kernel_share_of_step": kern_ms_all / max(world, 1) / ms_max,
+                         "peak_source": "measured live (hlm_measure_fma_peak)"},
+            "cpu_baseline": None, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def workload_config(args, ns):
     return {"workload": "Model204 hillslope-link runoff, synthetic links (SURVEY 8(d) inputs), 1-year hourly "
                         "pr + daily t2m forcing grid, hourly dense output; one step = one simulated day "
@@ -227,6 +380,15 @@ def main():
         PRM6[1] = args.rtol
     if args.atol is not None:
         PRM6[2] = args.atol
+    if args.links_per_gpu is None:
+        args.links_per_gpu = 10_000_000 if args.workload == "model204" else 2_500_000
+    if args.workload == "routed":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference couples no links (SURVEY 8(a) row 9): "
+                              "there is no reference implementation of the routed workload"}))
+            return
+        run_routed_arm(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return
