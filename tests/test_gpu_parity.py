@@ -248,11 +248,11 @@ def test_attempt_budget_reports_stalled(solver):
 
 
 def test_errors_are_loud(solver):
-    from tiger_hlm_gpu_b190 import HlmError
+    from tiger_hlm_gpu_b200 import HlmError
     with pytest.raises(HlmError, match="unknown model uid"):
         solver.set_model_parameters(190, Parameters())
     with pytest.raises(HlmError, match="unknown model uid"):
-        solver.run_rk45(200, np.ones((4, 5)), 0.0, 1.0, None)
+        solver.run_rk45(190, np.ones((4, 5)), 0.0, 1.0, None)
     solver.upload_spatial_params(synthetic.make_spatial_params(10))
     solver.clear_forcings()
     with pytest.raises(HlmError, match="exactly ns SpatialParams"):
