@@ -484,22 +484,24 @@ def main():
         y_host = torch.from_numpy(y0.copy()).pin_memory()
         f_host = torch.zeros((ns, 5), dtype=torch.float64).pin_memory()
         d_host = torch.zeros((ns, nq_w, 5), dtype=torch.float64).pin_memory()
-        stiff = np.zeros(ns, np.int32)
-        na = np.zeros(ns, np.int64)
+        stiff = torch.zeros(ns, dtype=torch.int32).pin_memory()
+        na = torch.zeros(ns, dtype=torch.int64).pin_memory()
         lib = hlm.load_library()
         import ctypes as C
+
+        bufs = [y_host, f_host]  # next day's initial state = this day's final state: the two pinned buffers swap roles
 
         def one_step(k):
             t0 = k * DAY
             tqw = t0 + 60.0 * np.arange(1, nq_w + 1)
-            rc = lib.hlm_run_rk45(solver._h, 204, C.c_void_p(y_host.data_ptr()), ns, t0, t0 + DAY,
-                                  tqw.ctypes.data_as(C.c_void_p), nq_w, C.c_void_p(f_host.data_ptr()),
-                                  C.c_void_p(d_host.data_ptr()), stiff.ctypes.data_as(C.c_void_p),
-                                  na.ctypes.data_as(C.c_void_p), None, None)
+            y_in, y_out = bufs[k % 2], bufs[(k + 1) % 2]
+            rc = lib.hlm_run_rk45(solver._h, 204, C.c_void_p(y_in.data_ptr()), ns, t0, t0 + DAY,
+                                  tqw.ctypes.data_as(C.c_void_p), nq_w, C.c_void_p(y_out.data_ptr()),
+                                  C.c_void_p(d_host.data_ptr()), C.c_void_p(stiff.data_ptr()),
+                                  C.c_void_p(na.data_ptr()), None, None)
             if rc != 0:
                 raise hlm.HlmError(lib.hlm_last_error().decode())
-            y_host.copy_(f_host)  # next day's initial state = this day's final state (host round trip)
-            return int(na.sum())
+            return int(na.sum().item())
 
         for k in range(W):
             one_step(k)

@@ -211,14 +211,26 @@ __global__ void restart_state_kernel(long long ld, double* __restrict__ t, doubl
     }
 }
 
-// final states back to the caller's [link][state] order; unfinished links give zeros
-__global__ void gather_final_kernel(const double* __restrict__ y, const int* __restrict__ status, int n_eq,
-                                    long long ns, long long ld, double* __restrict__ out_aos) {
+// session results in the caller's formats: final states back in [link][state] order (unfinished links give
+// zeros), counters widened to 64 bits, status as the HLM_LINK_* codes of hlm_b200.h
+__global__ void export_results_kernel(const double* __restrict__ y, const int* __restrict__ status,
+                                      const unsigned int* __restrict__ n_acc, const unsigned int* __restrict__ n_rej,
+                                      const unsigned int* __restrict__ n_jump, int n_eq, long long ns, long long ld,
+                                      double* __restrict__ out_aos, long long* __restrict__ out_cnt,
+                                      int* __restrict__ out_code) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
-    const bool ok = status[i] == hlm::kDone || status[i] == hlm::kDoneStiff;
-    for (int c = 0; c < n_eq; ++c) out_aos[i * n_eq + c] = ok ? y[(long long)c * ld + i] : 0.0;
+    const int s = status[i];
+    const bool ok = s == hlm::kDone || s == hlm::kDoneStiff;
+    if (out_aos)
+        for (int c = 0; c < n_eq; ++c) out_aos[i * n_eq + c] = ok ? y[(long long)c * ld + i] : 0.0;
+    out_cnt[i] = (long long)n_acc[i];
+    out_cnt[ns + i] = (long long)n_rej[i];
+    out_cnt[2 * ns + i] = (long long)n_jump[i];
+    out_code[i] = (s == hlm::kStiff || s == hlm::kStiffPaused) ? HLM_LINK_STIFF
+                  : (s == hlm::kDone ? HLM_LINK_OK : (s == hlm::kDoneStiff ? HLM_LINK_STIFF_SOLVED : HLM_LINK_STALLED));
 }
+
 
 __global__ void totals_kernel(const unsigned int* __restrict__ n_acc, const unsigned int* __restrict__ n_rej,
                               const unsigned int* __restrict__ n_jump, const int* __restrict__ status,
@@ -866,48 +878,33 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_end: no session");
     if (int r = use_device(c)) return r;
     const long long ns = c->ns;
-    if (out_final) {
-        // the window buffer not used last is free to stage the transposed final states
+    if (out_final || out_stiff || out_acc || out_rej || out_jump) {
+        // The window buffer not used last stages everything in the caller's formats (final states back in
+        // [link][state] order, counters widened to 64 bits, status as HLM_LINK_* codes), so each output is
+        // one device-to-host copy straight into the caller's array and the host touches no element.
         const int buf = c->dense_cur ^ 1;
         if (c->copy_pending[buf]) {
             HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
             c->copy_pending[buf] = false;
         }
-        HLM_CUDA(c->dense[buf].reserve((size_t)ns * c->n_eq));
+        const size_t n_final = (size_t)ns * c->n_eq;
+        HLM_CUDA(c->dense[buf].reserve(n_final + 3 * (size_t)ns + (size_t)ns / 2 + 1));
+        double* d_final = c->dense[buf].p;
+        long long* d_cnt = reinterpret_cast<long long*>(d_final + n_final);
+        int* d_code = reinterpret_cast<int*>(d_cnt + 3 * (size_t)ns);
         const int tpb = 256;
-        gather_final_kernel<<<(unsigned)((ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, c->status.p, c->n_eq, ns,
-                                                                                   c->ld, c->dense[buf].p);
+        export_results_kernel<<<(unsigned)((ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+            c->y.p, c->status.p, c->n_acc.p, c->n_rej.p, c->n_jump.p, c->n_eq, ns, c->ld, out_final ? d_final : nullptr, d_cnt,
+            d_code);
         HLM_CUDA(cudaGetLastError());
         ++c->launches;
-        HLM_CUDA(cudaMemcpyAsync(out_final, c->dense[buf].p, sizeof(double) * (size_t)ns * c->n_eq,
-                                 cudaMemcpyDeviceToHost, c->stream));
-    }
-    std::vector<unsigned int> tmp;
-    std::vector<int> st;
-    try {
-        if (out_acc || out_rej || out_jump) tmp.resize((size_t)ns);
-        if (out_stiff) st.resize((size_t)ns);
-    } catch (const std::bad_alloc&) {
-        return fail(HLM_ERR_NOMEM, "hlm_solve_end: out of host memory");
-    }
-    auto fetch = [&](const unsigned int* dev, long long* out) -> int {
-        if (!out) return 0;
-        HLM_CUDA(cudaMemcpyAsync(tmp.data(), dev, sizeof(unsigned int) * (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
-        HLM_CUDA(cudaStreamSynchronize(c->stream));
-        for (long long i = 0; i < ns; ++i) out[i] = (long long)tmp[(size_t)i];
-        return 0;
-    };
-    if (int r = fetch(c->n_acc.p, out_acc)) return r;
-    if (int r = fetch(c->n_rej.p, out_rej)) return r;
-    if (int r = fetch(c->n_jump.p, out_jump)) return r;
-    if (out_stiff) {
-        HLM_CUDA(cudaMemcpyAsync(st.data(), c->status.p, sizeof(int) * (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
-        HLM_CUDA(cudaStreamSynchronize(c->stream));
-        for (long long i = 0; i < ns; ++i) {
-            const int s = st[(size_t)i];
-            out_stiff[i] = (s == hlm::kStiff || s == hlm::kStiffPaused) ? HLM_LINK_STIFF
-                           : (s == hlm::kDone ? HLM_LINK_OK : (s == hlm::kDoneStiff ? HLM_LINK_STIFF_SOLVED : HLM_LINK_STALLED));
-        }
+        if (out_final) HLM_CUDA(cudaMemcpyAsync(out_final, d_final, sizeof(double) * n_final, cudaMemcpyDeviceToHost, c->stream));
+        long long* outs[3] = {out_acc, out_rej, out_jump};
+        for (int k = 0; k < 3; ++k)
+            if (outs[k])
+                HLM_CUDA(cudaMemcpyAsync(outs[k], d_cnt + (size_t)k * ns, sizeof(long long) * (size_t)ns, cudaMemcpyDeviceToHost,
+                                         c->stream));
+        if (out_stiff) HLM_CUDA(cudaMemcpyAsync(out_stiff, d_code, sizeof(int) * (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
     }
     HLM_CUDA(cudaStreamSynchronize(c->stream));
     HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
@@ -924,14 +921,35 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
         if (int r = hlm_solve_window(c, 0, 0)) return r;
     } else {
         const long long per_q = ns * c->n_eq * (long long)sizeof(double);
-        long long qw = std::max<long long>(1, c->dense_window_bytes / per_q);
-        long long n_win = (nq + qw - 1) / qw;
-        // a large transfer is cut into at least 6 windows so that all but the last window's D2H copy
-        // overlaps the next window's integration (two buffers, copy stream)
-        if (per_q * nq > (256LL << 20)) n_win = std::max<long long>(n_win, std::min<long long>(6, nq));
-        qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
-        for (long long q = 0; q < nq;) {
-            q = std::min(nq, q + qw);
+        const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
+        long long n_win = (nq + qw_max - 1) / qw_max;
+        std::vector<long long> cuts;  // window ends
+        if (per_q * nq > (256LL << 20) && nq >= 2) {
+            // A large transfer: all but the last window's D2H copy overlaps the next window's integration (two
+            // buffers, copy stream), so windows shrink towards the end — sizes fall linearly, which keeps each
+            // copy shorter than the integration it hides behind as long as the link is not much slower than the
+            // kernel — and what stays exposed is the copy of a last, small window.
+            n_win = std::max<long long>(n_win, std::min<long long>(7, nq));
+            const double total_w = 0.5 * (double)n_win * (double)(n_win + 1);
+            double acc_w = 0.0;
+            for (long long i = 0; i < n_win; ++i) {
+                acc_w += (double)(n_win - i);
+                long long end = (long long)std::llround((double)nq * acc_w / total_w);
+                const long long prev = cuts.empty() ? 0 : cuts.back();
+                if (prev >= nq) break;
+                end = std::min(nq, std::max(end, prev + 1));
+                end = std::min(end, prev + qw_max);
+                cuts.push_back(end);
+            }
+            while (cuts.back() < nq) cuts.push_back(std::min(nq, cuts.back() + qw_max));
+        } else {
+            const long long qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
+            for (long long q = 0; q < nq;) {
+                q = std::min(nq, q + qw);
+                cuts.push_back(q);
+            }
+        }
+        for (long long q : cuts) {
             if (int r = hlm_solve_window(c, q, 1)) return r;
             if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
         }
