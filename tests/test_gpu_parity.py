@@ -164,6 +164,26 @@ def test_windowed_run_is_bit_identical_to_single_window(solver):
     assert_same_result(a, c, exact=True)
 
 
+def test_link_chunked_run_is_bit_identical_to_single_window(solver):
+    """hlm_run_rk45 cuts a large output into chunks of links (each one contiguous block of the caller's
+    array, copied while the next chunk integrates); ragged last chunk, ns not a multiple of 32."""
+    ns, days = 3011, 1
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.3)
+    tq = synthetic.hourly_queries(0.0, 1440.0)
+    solver.set_dense_window_bytes(8 << 30)
+    n0 = solver.launch_count()
+    a = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
+    one = solver.launch_count() - n0
+    solver.set_dense_window_bytes(len(tq) * 5 * 8 * 32 * 10)      # at most 10 tiles = 320 links per chunk
+    n0 = solver.launch_count()
+    b = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
+    assert solver.launch_count() - n0 >= one + 8                  # >= 10 window kernels (parameters are prepared once)
+    solver.set_dense_window_bytes(8 << 30)
+    assert_same_result(a, b, exact=True)
+    o = orun(204, OPRM, y0, 0.0, 1440.0, tq, sp=sp, forcing=forcing, threads=8)
+    assert_same_result(b, o, exact=True)
+
+
 def test_windows_with_steps_longer_than_the_query_spacing(solver, golden_dummy):
     """DummyModel takes 12 steps for 10 000 queries: every window boundary falls inside a step, which
     exercises the leave-uncommitted-and-redo path."""

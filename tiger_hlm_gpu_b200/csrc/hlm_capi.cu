@@ -347,8 +347,7 @@ template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::Wind
         HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hlm::rk45_window_kernel<Model, T>, 128, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
-    const long long n_tiles = (a.ns + 31) / 32;
-    long long grid = std::min<long long>((n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm);
+    long long grid = std::min<long long>((a.n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm);
     if (grid < 1) grid = 1;
     HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
@@ -689,41 +688,10 @@ static int restart_impl(hlm_ctx* c, double t0, double tf, const double* tq, long
     return HLM_OK;
 }
 
-int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
-    HLM_REQUIRE(c, "hlm_solve_window: ctx is NULL");
-    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_window: no session (call hlm_solve_begin)");
-    if (int r = use_device(c)) return r;
-    if (q_hi > c->nq) q_hi = c->nq;
-    HLM_REQUIRE(q_hi >= c->q_done, "hlm_solve_window: q_hi must not move backwards");
-    // a chunked forcing record must cover every sample the interval [t0, tf] can index
-    // (size_t(t / (dt*60)) clamped to the record, solver/rk45_kernel.cu:90-98)
-    if (const ModelInfo* m = find_model(c->uid))
-        for (int j = 0; j < std::min(c->n_forc, m->n_forc); ++j) {
-            const double dtm = c->forc_dt_h[j] * 60.0;
-            if (!(dtm > 0.0) || c->forc_nres[j] == c->forc_nT[j]) continue;
-            auto index = [&](double t) {
-                const double r = t / dtm;
-                return (r < 0.0) ? 0LL : (r >= (double)c->forc_nT[j] ? c->forc_nT[j] - 1 : (long long)r);
-            };
-            if (index(c->t0) < c->forc_i0[j] || index(c->tf) >= c->forc_i0[j] + c->forc_nres[j])
-                return fail(HLM_ERR_STATE, "hlm_solve_window: the resident chunk of forcing " + std::to_string(j) +
-                                               " does not cover the interval");
-        }
-    const long long q_lo = c->q_done;
-    const long long qw = q_hi - q_lo;
-    const bool dense = want_dense && qw > 0;
-    int buf = c->dense_cur;
-    if (dense) {
-        buf = c->dense_cur ^ 1;
-        if (c->copy_pending[buf]) {  // the D2H that last read this buffer must finish before it is overwritten
-            HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
-            c->copy_pending[buf] = false;
-        }
-        const size_t elems = (size_t)c->ns * (size_t)qw * (size_t)c->n_eq;
-        HLM_CUDA(c->dense[buf].reserve(elems));
-        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
-        c->dense_cur = buf;
-    }
+// Queue the window kernel (and the implicit fallback, if on) for queries [q_lo, q_hi) over the links of tiles
+// [tile_lo, tile_lo + n_tiles); `dense` (may be NULL) receives the records, row 0 = link dense_sys0.
+static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, double* dense, long long tile_lo, long long n_tiles,
+                        long long dense_sys0) {
     hlm::WindowArgs a;
     std::memset(&a, 0, sizeof(a));
     a.y = c->y.p; a.t = c->t.p; a.h = c->h.p; a.next_q = c->next_q.p; a.reject_run = c->reject_run.p;
@@ -743,10 +711,11 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     a.nq = (int)c->nq;
     a.q_lo = (int)q_lo;
     a.q_hi = (int)q_hi;
-    a.dense = dense ? c->dense[buf].p : nullptr;
+    a.dense = dense;
     a.t0 = c->t0; a.tf = c->tf;
     a.prm = c->params[c->uid];
     a.ns = c->ns; a.ld = c->ld;
+    a.tile_lo = tile_lo; a.n_tiles = n_tiles; a.dense_sys0 = dense_sys0;
     a.max_attempts = c->max_attempts;
     a.tile_counter = c->tile_counter.p;
     if (c->routed) {
@@ -758,6 +727,50 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
     if (int r = dispatch_window(c, a)) return r;
     if (c->stiff_fallback)
         if (int r = dispatch_radau(c, a)) return r;
+    return 0;
+}
+
+// a chunked forcing record must cover every sample the interval [t0, tf] can index
+// (size_t(t / (dt*60)) clamped to the record, solver/rk45_kernel.cu:90-98)
+static int check_forcing_cover(hlm_ctx* c) {
+    if (const ModelInfo* m = find_model(c->uid))
+        for (int j = 0; j < std::min(c->n_forc, m->n_forc); ++j) {
+            const double dtm = c->forc_dt_h[j] * 60.0;
+            if (!(dtm > 0.0) || c->forc_nres[j] == c->forc_nT[j]) continue;
+            auto index = [&](double t) {
+                const double r = t / dtm;
+                return (r < 0.0) ? 0LL : (r >= (double)c->forc_nT[j] ? c->forc_nT[j] - 1 : (long long)r);
+            };
+            if (index(c->t0) < c->forc_i0[j] || index(c->tf) >= c->forc_i0[j] + c->forc_nres[j])
+                return fail(HLM_ERR_STATE, "hlm_solve_window: the resident chunk of forcing " + std::to_string(j) +
+                                               " does not cover the interval");
+        }
+    return 0;
+}
+
+int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
+    HLM_REQUIRE(c, "hlm_solve_window: ctx is NULL");
+    if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_window: no session (call hlm_solve_begin)");
+    if (int r = use_device(c)) return r;
+    if (q_hi > c->nq) q_hi = c->nq;
+    HLM_REQUIRE(q_hi >= c->q_done, "hlm_solve_window: q_hi must not move backwards");
+    if (int r = check_forcing_cover(c)) return r;
+    const long long q_lo = c->q_done;
+    const long long qw = q_hi - q_lo;
+    const bool dense = want_dense && qw > 0;
+    int buf = c->dense_cur;
+    if (dense) {
+        buf = c->dense_cur ^ 1;
+        if (c->copy_pending[buf]) {  // the D2H that last read this buffer must finish before it is overwritten
+            HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
+            c->copy_pending[buf] = false;
+        }
+        const size_t elems = (size_t)c->ns * (size_t)qw * (size_t)c->n_eq;
+        HLM_CUDA(c->dense[buf].reserve(elems));
+        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
+        c->dense_cur = buf;
+    }
+    if (int r = queue_window(c, q_lo, q_hi, dense ? c->dense[buf].p : nullptr, 0, (c->ns + 31) / 32, 0)) return r;
     c->q_done = q_hi;
     c->win_q_lo = q_lo;
     c->win_q_hi = q_hi;
@@ -912,6 +925,51 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
     return HLM_OK;
 }
 
+// All queries of a large run, chunk of links by chunk of links: each chunk's records form one contiguous block
+// of the caller's [link][query][state] array, so every device-to-host copy is a plain memcpy at full link
+// rate (windows over queries leave as 2-D copies of short rows), and it overlaps the next chunk's integration
+// (two buffers, copy stream).  Chunks shrink towards the end: what stays exposed is the copy of a small last one.
+static int run_link_chunks(hlm_ctx* c, double* out_dense) {
+    const long long ns = c->ns, nq = c->nq;
+    const long long per_link = nq * c->n_eq * (long long)sizeof(double);
+    const long long n_tiles_all = (ns + 31) / 32;
+    const long long tiles_max = std::max<long long>(1, c->dense_window_bytes / (per_link * 32));
+    long long n_chunks = std::max<long long>((n_tiles_all + tiles_max - 1) / tiles_max, std::min<long long>(8, n_tiles_all));
+    if (int r = check_forcing_cover(c)) return r;
+    const double total_w = 0.5 * (double)n_chunks * (double)(n_chunks + 1);
+    double acc_w = 0.0;
+    long long tile = 0;
+    for (long long i = 0; tile < n_tiles_all; ++i) {
+        acc_w += (double)std::max<long long>(n_chunks - i, 1);
+        long long end = (long long)std::llround((double)n_tiles_all * std::min(1.0, acc_w / total_w));
+        end = std::min(n_tiles_all, std::max(end, tile + 1));
+        end = std::min(end, tile + tiles_max);
+        const long long lo = tile * 32, hi = std::min(ns, end * 32);
+        const int buf = c->dense_cur ^ 1;
+        if (c->copy_pending[buf]) {
+            HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
+            c->copy_pending[buf] = false;
+        }
+        const size_t elems = (size_t)(hi - lo) * (size_t)nq * (size_t)c->n_eq;
+        HLM_CUDA(c->dense[buf].reserve(elems));
+        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
+        c->dense_cur = buf;
+        if (int r = queue_window(c, 0, nq, c->dense[buf].p, tile, end - tile, lo)) return r;
+        HLM_CUDA(cudaEventRecord(c->ev_kernel_done[buf], c->stream));
+        HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
+        HLM_CUDA(cudaMemcpyAsync(out_dense + (size_t)lo * nq * c->n_eq, c->dense[buf].p, elems * sizeof(double),
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+        HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
+        c->copy_pending[buf] = true;
+        tile = end;
+    }
+    c->q_done = nq;
+    c->win_q_lo = 0;
+    c->win_q_hi = nq;
+    c->win_has_dense = false;  // the buffers hold chunks of links, not a window a caller could fetch
+    return HLM_OK;
+}
+
 int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
                  long long nq, double* out_final, double* out_dense, int* out_stiff, long long* out_acc,
                  long long* out_rej, long long* out_jump) {
@@ -921,37 +979,20 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
         if (int r = hlm_solve_window(c, 0, 0)) return r;
     } else {
         const long long per_q = ns * c->n_eq * (long long)sizeof(double);
-        const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
-        long long n_win = (nq + qw_max - 1) / qw_max;
-        std::vector<long long> cuts;  // window ends
-        if (per_q * nq > (256LL << 20) && nq >= 2) {
-            // A large transfer: all but the last window's D2H copy overlaps the next window's integration (two
-            // buffers, copy stream), so windows shrink towards the end — sizes fall linearly, which keeps each
-            // copy shorter than the integration it hides behind as long as the link is not much slower than the
-            // kernel — and what stays exposed is the copy of a last, small window.
-            n_win = std::max<long long>(n_win, std::min<long long>(7, nq));
-            const double total_w = 0.5 * (double)n_win * (double)(n_win + 1);
-            double acc_w = 0.0;
-            for (long long i = 0; i < n_win; ++i) {
-                acc_w += (double)(n_win - i);
-                long long end = (long long)std::llround((double)nq * acc_w / total_w);
-                const long long prev = cuts.empty() ? 0 : cuts.back();
-                if (prev >= nq) break;
-                end = std::min(nq, std::max(end, prev + 1));
-                end = std::min(end, prev + qw_max);
-                cuts.push_back(end);
-            }
-            while (cuts.back() < nq) cuts.push_back(std::min(nq, cuts.back() + qw_max));
+        const long long per_link = nq * c->n_eq * (long long)sizeof(double);
+        if (per_q * nq > std::min<long long>(256LL << 20, c->dense_window_bytes) && per_link * 32 <= c->dense_window_bytes) {
+            if (int r = run_link_chunks(c, out_dense)) return r;
         } else {
+            // small output (one window), or a query list so long that even 32 links of it exceed a buffer:
+            // windows over queries
+            const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
+            const long long n_win = (nq + qw_max - 1) / qw_max;
             const long long qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
             for (long long q = 0; q < nq;) {
                 q = std::min(nq, q + qw);
-                cuts.push_back(q);
+                if (int r = hlm_solve_window(c, q, 1)) return r;
+                if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
             }
-        }
-        for (long long q : cuts) {
-            if (int r = hlm_solve_window(c, q, 1)) return r;
-            if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
         }
     }
     return hlm_solve_end(c, out_final, out_stiff, out_acc, out_rej, out_jump);

@@ -14,7 +14,8 @@ static cudaError_t radau_launch_model(const WindowArgs& a, int* list, unsigned i
     cudaError_t e = cudaMemsetAsync(n_list, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     const int tpb = 256;
-    radau_collect_kernel<<<(unsigned)((a.ns + tpb - 1) / tpb), tpb, 0, stream>>>(a.status, a.ns, list, n_list);
+    const long long lo = a.tile_lo << 5, hi = std::min<long long>(a.ns, (a.tile_lo + a.n_tiles) << 5);
+    radau_collect_kernel<<<(unsigned)((hi - lo + tpb - 1) / tpb), tpb, 0, stream>>>(a.status, lo, hi, list, n_list);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     RadauArgs ra;
     ra.w = a;
@@ -22,7 +23,7 @@ static cudaError_t radau_launch_model(const WindowArgs& a, int* list, unsigned i
     ra.n_list = n_list;
     ra.n_radau = n_radau;
     // the list length lives on the device: a fixed grid strides over it (flagged links are rare)
-    const unsigned grid = (unsigned)std::min<long long>((a.ns + 63) / 64, (long long)sm_count * 4);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((hi - lo + 63) / 64, (long long)sm_count * 4));
     radau_window_kernel<Model><<<grid, 64, 0, stream>>>(ra);
     return cudaGetLastError();
 }

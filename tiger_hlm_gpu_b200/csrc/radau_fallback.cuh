@@ -82,10 +82,10 @@ struct RadauArgs {
 };
 
 // status kStiff -> list (order is arbitrary; every link's result depends on that link alone)
-__global__ void radau_collect_kernel(const int* __restrict__ status, long long ns, int* __restrict__ list,
+__global__ void radau_collect_kernel(const int* __restrict__ status, long long lo, long long hi, int* __restrict__ list,
                                      unsigned int* __restrict__ n_list) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ns && (status[i] == kStiff || status[i] == kStiffPaused)) list[atomicAdd(n_list, 1u)] = (int)i;
+    const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hi && (status[i] == kStiff || status[i] == kStiffPaused)) list[atomicAdd(n_list, 1u)] = (int)i;
 }
 
 template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel(const RadauArgs ra) {
@@ -230,7 +230,7 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
                     if (next_q >= a.q_hi) { overshoot = true; break; }
                     if (tq > t && a.dense != nullptr) {
                         const double th = (tq - t) / h;
-                        double* out = a.dense + ((long long)sys * qw + (next_q - a.q_lo)) * N;
+                        double* out = a.dense + ((sys - a.dense_sys0) * qw + (next_q - a.q_lo)) * N;
                         for (int i = 0; i < N; ++i) {
                             // collocation cubic through (0,0), (c1,Z1), (c2,Z2), (1,Z3): Newton form
                             const double d1 = Z[0][i] / C1, d2 = (Z[1][i] - Z[0][i]) / (C2 - C1), d3 = (Z[2][i] - Z[1][i]) / (1.0 - C2);

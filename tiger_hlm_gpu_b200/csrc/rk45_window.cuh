@@ -149,6 +149,10 @@ struct WindowArgs {
     double t0, tf;
     SolverParams prm;
     long long ns, ld;
+    // links of this launch: tiles [tile_lo, tile_lo + n_tiles) of 32 links; dense records of link sys go to
+    // row sys - dense_sys0 of the buffer (a launch over a chunk of links fills a buffer of its own, which
+    // then leaves in one contiguous copy)
+    long long tile_lo, n_tiles, dense_sys0;
     long long max_attempts;  // per link per launch; <=0 = unbounded like the reference
     unsigned int* tile_counter;
     // routed models (Model::HAS_INFLOW): discharge entering each link from upstream, constant over the
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const int lane = threadIdx.x & 31;
-    const long long n_tiles = (a.ns + 31) >> 5;
+    const long long n_tiles = a.n_tiles;
     const bool run_to_end = (a.q_hi >= a.nq);
     const int qw = a.q_hi - a.q_lo;
     const T rtol = (T)a.prm.rtol, atol = (T)a.prm.atol;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if ((long long)tile >= n_tiles) break;
-        const long long sys = ((long long)tile << 5) + lane;
+        const long long sys = ((a.tile_lo + (long long)tile) << 5) + lane;
         if (sys >= a.ns) continue;
         int status = a.status[sys];
         if (status != kActive) continue;
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                         if (next_q >= a.q_hi) { overshoot = true; break; }
                         if (tq_next > t && a.dense != nullptr) {
                             const T th = f::div(f::sub(tq_next, t), h);
-                            double* out = a.dense + ((long long)sys * qw + (next_q - a.q_lo)) * N;
+                            double* out = a.dense + ((sys - a.dense_sys0) * qw + (next_q - a.q_lo)) * N;
                             const T th2 = f::mul(th, th), th3 = f::mul(th2, th), th4 = f::mul(th3, th);
 #pragma unroll
                             for (int i = 0; i < N; ++i) {
