@@ -81,6 +81,9 @@ class Context {
         check(hlm_set_forcing_columns(ctx_, col, n), "hlm_set_forcing_columns");
     }
     void clearForcings() { check(hlm_clear_forcings(ctx_), "hlm_clear_forcings"); }
+    /// Links the RK45 path flags stiff are carried on by the Radau IIA fallback (run_rk45's documented
+    /// behaviour, solver/rk45_api.hpp:198-247) instead of being abandoned; they come back as HLM_LINK_STIFF_SOLVED.
+    void setStiffFallback(bool on) { check(hlm_set_stiff_fallback(ctx_, on ? 1 : 0), "hlm_set_stiff_fallback"); }
 
     struct Result {
         std::vector<double> final_state;  // [ns][N_EQ]
@@ -120,6 +123,12 @@ inline Context& default_context() {
 struct Model204 {
     using SP_TYPE = SpatialParams;
     static constexpr unsigned short UID = 204;  // models/model_204.hpp:18
+    static constexpr int N_EQ = 5;
+    using Parameters = hlm_b200::Parameters;
+};
+struct Model200 {  // named by the reference (README.md:95) but not defined there: project-defined, see hlm_b200.h
+    using SP_TYPE = SpatialParams;
+    static constexpr unsigned short UID = 200;
     static constexpr int N_EQ = 5;
     using Parameters = hlm_b200::Parameters;
 };

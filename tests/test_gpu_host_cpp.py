@@ -37,3 +37,36 @@ def test_cpp_example_writes_reference_format_csvs(tmp_path, small_test_params, g
     np.testing.assert_allclose(got, o["dense"], rtol=2e-9, atol=5e-10)   # dense.csv: setprecision(9) fixed
     tol = 10 * (1e-9 + 1e-6 * np.abs(golden204["final"]))
     assert np.all(np.abs(final - golden204["final"]) <= tol + 2e-6 * np.abs(golden204["final"]))
+
+
+def test_cpp_routed_example_matches_the_routed_oracle(tmp_path):
+    """hlm_routed_example: parameter CSV with a river network -> hlm_b200::plan_routes -> RoutedRun (Model 200,
+    coupling intervals, implicit fallback) -> final.csv/dense.csv, against the CPU routed run."""
+    from tests import routed_ref
+    from tiger_hlm_gpu_b200 import routing
+    from tiger_hlm_gpu_b200.hostio import load_spatial_params, write_spatial_params_csv
+    exe = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host", "build", "hlm_routed_example")
+    ns, hours, dt, sub = 600, 3.0, 15.0, 64
+    sp = synthetic.apply_network(synthetic.make_spatial_params(ns), synthetic.make_network(ns, subbasin_links=sub, seed=3))
+    csv = str(tmp_path / "params.csv")
+    write_spatial_params_csv(csv, sp)
+    sp = load_spatial_params(csv)                       # what the C++ loader sees (unit conversions round-tripped)
+    r = subprocess.run([exe, csv, str(tmp_path), str(hours), str(dt), str(sub), "4", "2e-5", "8.0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p4 = routing.plan(sp["stream"], sp["next_stream"], 4, subbasin_links=sub)
+    assert f"{p4.n_subbasins} sub-basins, {p4.n_cut_edges} cut edges, halo vector of {p4.halo_len} doubles" in r.stdout
+    assert " 0 lost" in r.stdout
+    final = np.loadtxt(tmp_path / "final.csv", delimiter=",", skiprows=1)
+    dense = np.loadtxt(tmp_path / "dense.csv", delimiter=",", skiprows=1)
+    n_int = int(hours * 60 / dt)
+    assert dense.shape == (n_int, 1 + ns * 5)
+    pr = np.full((int(hours + 1.5), ns), 2e-5, np.float32)
+    t2m = np.full((1, ns), 8.0, np.float32)
+    y0 = np.tile(synthetic.Y0_200, (ns, 1))
+    p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=sub)
+    fin_o, dense_o, tq_o, _ = routed_ref.run_single(sp, O.Forcing([pr, t2m], [1.0, 24.0]), y0, O.Params.make(initialStep=1e-6), p1,
+                                                    0.0, hours * 60.0, dt, threads=8)
+    assert np.array_equal(dense[:, 0], tq_o)
+    np.testing.assert_allclose(final, fin_o, rtol=2e-6)                                    # 6 significant digits in final.csv
+    np.testing.assert_allclose(dense[:, 1:].reshape(n_int, ns, 5).transpose(1, 0, 2), dense_o, rtol=2e-9, atol=5e-10)
+    assert fin_o[:, 0].max() > 5 * fin_o[:, 0].min()                                        # discharge accumulates downstream

@@ -7,6 +7,7 @@
 
 #include "hlm_config.hpp"
 #include "hlm_netcdf.hpp"
+#include "hlm_routing.hpp"
 
 namespace {
 thread_local std::string g_err, g_text;
@@ -130,6 +131,36 @@ const char* hlmio_load_config_json(const char* path) {
         }))
         return nullptr;
     return g_text.c_str();
+}
+
+
+/// hlm_b200::plan_routes flattened for the tests.  order[n]; rank_lo[world + 1]; up_ptr_all: every rank's
+/// up_ptr one after the other (n + world entries); up_idx_all / send_idx_all: every rank's lists one after the
+/// other (at most n entries each); send_counts[world]; meta = {max_send, n_subbasins, n_cut_edges}.
+int hlmio_route_plan(const long long* stream, const long long* next_stream, long long n, int world, long long subbasin_links,
+                     long long* order, long long* rank_lo, long long* up_ptr_all, int* up_idx_all, int* send_idx_all,
+                     long long* send_counts, long long* meta) {
+    return guarded([&] {
+        std::vector<long long> s(stream, stream + n), nx(next_stream, next_stream + n);
+        const hlm_b200::RoutePlan p = hlm_b200::plan_routes(s, nx, world, subbasin_links);
+        std::copy(p.order.begin(), p.order.end(), order);
+        long long a = 0, b = 0, c = 0;
+        for (int r = 0; r < world; ++r) {
+            const hlm_b200::RankTopology& t = p.ranks[(size_t)r];
+            rank_lo[r] = t.lo;
+            rank_lo[r + 1] = t.hi;
+            std::copy(t.up_ptr.begin(), t.up_ptr.end(), up_ptr_all + a);
+            a += (long long)t.up_ptr.size();
+            std::copy(t.up_idx.begin(), t.up_idx.end(), up_idx_all + b);
+            b += (long long)t.up_idx.size();
+            std::copy(t.send_idx.begin(), t.send_idx.end(), send_idx_all + c);
+            c += (long long)t.send_idx.size();
+            send_counts[r] = (long long)t.send_idx.size();
+        }
+        meta[0] = p.max_send;
+        meta[1] = p.n_subbasins;
+        meta[2] = p.n_cut_edges;
+    });
 }
 
 }  // extern "C"

@@ -70,3 +70,20 @@ def load_lookup(csv_path: str) -> dict[int, tuple[int, int]]:
             if len(p) >= 3:
                 out[int(p[0])] = (int(p[1]), int(p[2]))
     return out
+
+
+def write_spatial_params_csv(path: str, sp: np.ndarray, lon=None) -> None:
+    """A parameter CSV with the columns I_O/parameters_loader.cpp:35-49 requires, from SpatialParams records
+    (inverse of the loader's unit conversions: i2 = infil / c1, res_ss = alpha3 / 1440, ...)."""
+    c1 = 0.001 / 60.0
+    cols = ["stream", "next_stream", "drainage_area_km2", "length_km", "area_sqkm", "centroid_lon", "centroid_lat", "hu",
+            "i2", "i3", "sw", "ss", "n", "slope", "res_ss", "res_gw", "melt", "t_thres"]
+    with open(path, "w") as f:
+        f.write(",".join(cols) + "\n")
+        for k, r in enumerate(sp):
+            vals = [int(r["stream"]), int(r["next_stream"]), repr(float(r["A_h"])), repr(float(r["L"])), repr(float(r["A_h"])),
+                    repr(float(lon[k]) if lon is not None else -75.0), repr(float(r["lat"])), repr(float(r["Hu"])),
+                    repr(float(r["infil"] / c1)), repr(float(r["perco"] / c1)), repr(float(r["sw"])), repr(float(r["ss"])),
+                    repr(float(r["n_mann"])), repr(float(r["slope"])), repr(float(r["alpha3"] / 1440.0)),
+                    repr(float(r["alpha4"] / 1440.0)), repr(float(r["melt_f"])), repr(float(r["temp_thr"]))]
+            f.write(",".join(str(v) for v in vals) + "\n")
