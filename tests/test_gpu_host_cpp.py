@@ -67,6 +67,6 @@ def test_cpp_routed_example_matches_the_routed_oracle(tmp_path):
     fin_o, dense_o, tq_o, _ = routed_ref.run_single(sp, O.Forcing([pr, t2m], [1.0, 24.0]), y0, O.Params.make(initialStep=1e-6), p1,
                                                     0.0, hours * 60.0, dt, threads=8)
     assert np.array_equal(dense[:, 0], tq_o)
-    np.testing.assert_allclose(final, fin_o, rtol=2e-6)                                    # 6 significant digits in final.csv
+    np.testing.assert_allclose(final, fin_o, rtol=6e-6)                                    # 6 significant digits in final.csv
     np.testing.assert_allclose(dense[:, 1:].reshape(n_int, ns, 5).transpose(1, 0, 2), dense_o, rtol=2e-9, atol=5e-10)
     assert fin_o[:, 0].max() > 5 * fin_o[:, 0].min()                                        # discharge accumulates downstream
