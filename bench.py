@@ -417,6 +417,8 @@ def main():
     ns = args.links_per_gpu
     K, W = args.steps, args.warmup
     assert W + K <= args.days, "not enough forcing days for warmup+steps"
+    from tiger_hlm_gpu_b200.sharding import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
 
     sp, col, ncells, pr, t2m, y0 = make_inputs(ns, args.days, args.wet_fraction, rank)
     solver = hlm.Solver(local_rank)
@@ -583,7 +585,7 @@ def main():
                          "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_window_kernel<Model204,double>",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_link_per_launch": bytes_per_link}},
-            "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks,
+            "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks, "host_binding": numa,
         }
         print(json.dumps(line), flush=True)
     solver.close()
