@@ -56,6 +56,8 @@ def parse_args():
                          "through upstream discharge, partitioned by sub-basin, boundary links exchanged over NCCL")
     ap.add_argument("--links-per-gpu", type=int, default=None, help="default 10M (model204) / 2.5M (routed)")
     ap.add_argument("--couple-minutes", type=float, default=15.0, help="routed: coupling interval")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes"],
+                    help="how links are dealt to lanes (hlm_set_schedule); auto = lanes for routed runs, tiles otherwise")
     ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
     ap.add_argument("--wet-fraction", type=float, default=0.0,
                     help="share of links started with surface storage so Model204's pow() branch runs")
@@ -260,6 +262,7 @@ def run_routed_arm(args):
     y0[:, 0] = rng.uniform(0.05, 5.0, ns_all)[sel]
     solver = hlm.Solver(local_rank)
     solver.set_model_parameters(200, hlm.Parameters(*PRM6))
+    solver.set_schedule(args.schedule)
     solver.set_max_attempts(5_000_000)
     solver.upload_spatial_params(sp_all[sel])
     solver.upload_forcing(0, 1.0, pr)
@@ -341,7 +344,7 @@ def run_routed_arm(args):
                                    "river network, links coupled through upstream discharge held over a coupling interval; "
                                    "one step = one simulated hour",
                        "links_per_gpu": args.links_per_gpu, "links_total": ns_all, "couple_minutes": dt,
-                       "intervals_per_step": n_int, "sub_basins": plan.n_subbasins, "cut_edges": plan.n_cut_edges,
+                       "intervals_per_step": n_int, "schedule": args.schedule, "sub_basins": plan.n_subbasins, "cut_edges": plan.n_cut_edges,
                        "halo_doubles": plan.halo_len, "rtol": PRM6[1], "atol": PRM6[2],
                        "parallelism": f"sub-basins dealt to {world} GPU(s); one NCCL all-gather of the boundary vector per interval"
                                       if world > 1 else "1 GPU, no exchange",
@@ -429,6 +432,7 @@ def main():
     assert stream.cuda_stream != 0
     solver.set_stream(stream.cuda_stream)
     solver.set_precision(args.precision)
+    solver.set_schedule(args.schedule)
     solver.set_model_parameters(204, hlm.Parameters(*PRM6))
     solver.set_max_attempts(5_000_000)
     solver.upload_spatial_params(sp)

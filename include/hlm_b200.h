@@ -128,6 +128,15 @@ int hlm_set_dense_window_bytes(hlm_ctx* ctx, long long bytes);
  * radau_kernel_multi in run_rk45 (solver/rk45_api.hpp:198-247, solver/radau_kernel.cu:20-140), with the
  * numerics done properly (csrc/radau_fallback.cuh says what was kept and what was replaced).  FP64 only. */
 int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
+/* How links are dealt to lanes.  TILES: a warp takes 32 consecutive links and stays with them until the slowest
+ * is done — right when neighbouring links step alike (links sorted by forcing cell).  LANES: a lane takes the
+ * next unclaimed link the moment it is done with its own, so a warp never idles behind its slowest link —
+ * right when links take unlike numbers of attempts per launch (routed runs with short coupling intervals).
+ * AUTO (default): LANES for routed runs, TILES otherwise.  Results are bit-identical under either. */
+#define HLM_SCHEDULE_AUTO 0
+#define HLM_SCHEDULE_TILES 1
+#define HLM_SCHEDULE_LANES 2
+int hlm_set_schedule(hlm_ctx* ctx, int mode);
 /* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */
 int hlm_set_precision(hlm_ctx* ctx, int bits);
 

@@ -184,6 +184,34 @@ def test_link_chunked_run_is_bit_identical_to_single_window(solver):
     assert_same_result(b, o, exact=True)
 
 
+def test_lane_refill_schedule_is_bit_identical_to_tiles(solver, golden_dummy):
+    """hlm_set_schedule: a lane takes the next unclaimed link when it is done with its own instead of waiting for
+    its tile.  Same per-link arithmetic, so the same bits — whole run, windowed, link-chunked, DummyModel."""
+    ns, days = 1237, 2
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.4)
+    tf = days * 1440.0
+    tq = synthetic.hourly_queries(0.0, tf)
+    a = solver.run_rk45(204, y0, 0.0, tf, tq)
+    try:
+        solver.set_schedule("lanes")
+        b = solver.run_rk45(204, y0, 0.0, tf, tq)
+        solver.set_dense_window_bytes(ns * 5 * 8 * 5)                   # windows of 5 queries
+        c = solver.run_rk45(204, y0, 0.0, tf, tq)
+        solver.set_dense_window_bytes(len(tq) * 5 * 8 * 32 * 7)          # chunks of 7 tiles
+        d = solver.run_rk45(204, y0, 0.0, tf, tq)
+        solver.set_dense_window_bytes(8 << 30)
+        solver.set_model_parameters(0, Parameters())
+        yd = np.ones((70, 5)) * np.linspace(0.5, 1.5, 70)[:, None]
+        e = solver.run_rk45(0, yd, 0.0, 5.0, golden_dummy["query_times"])
+    finally:
+        solver.set_schedule("auto")
+        solver.set_dense_window_bytes(8 << 30)
+    for other in (b, c, d):
+        assert_same_result(a, other, exact=True)
+    assert_same_result(e, orun(0, O.Params.make(), yd, 0.0, 5.0, golden_dummy["query_times"]), exact=True)
+    solver.set_model_parameters(204, PRM)
+
+
 def test_windows_with_steps_longer_than_the_query_spacing(solver, golden_dummy):
     """DummyModel takes 12 steps for 10 000 queries: every window boundary falls inside a step, which
     exercises the leave-uncommitted-and-redo path."""

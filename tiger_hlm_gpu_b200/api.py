@@ -51,6 +51,7 @@ SIGNATURES = {
     "hlm_set_max_attempts": (_I, [_V, _LL]),
     "hlm_set_dense_window_bytes": (_I, [_V, _LL]),
     "hlm_set_precision": (_I, [_V, _I]),
+    "hlm_set_schedule": (_I, [_V, _I]),
     "hlm_set_stiff_fallback": (_I, [_V, _I]),
     "hlm_solve_radau_steps": (_I, [_V, _V]),
     "hlm_run_rk45": (_I, [_V, _I, _V, _LL, _D, _D, _V, _LL, _V, _V, _V, _V, _V, _V]),
@@ -244,6 +245,10 @@ class Solver:
         out = np.zeros(self._session[2], np.int64)
         _check(self._lib.hlm_solve_radau_steps(self._h, _p(out)))
         return out
+
+    def set_schedule(self, mode: str = "auto"):
+        """'tiles', 'lanes' or 'auto' (lanes for routed runs) — hlm_set_schedule."""
+        _check(self._lib.hlm_set_schedule(self._h, {"auto": 0, "tiles": 1, "lanes": 2}[mode]))
 
     def set_precision(self, bits: int):
         _check(self._lib.hlm_set_precision(self._h, bits))

@@ -136,6 +136,8 @@ struct hlm_ctx {
     DevBuf<int> radau_list;
     DevBuf<unsigned int> radau_count, n_radau;
 
+    int schedule = HLM_SCHEDULE_AUTO;
+
     // routed runs (models with upstream inflow): topology of the links this context owns
     bool routed = false;
     long long route_ns = 0, route_nnz = 0, route_n_send = 0;
@@ -342,17 +344,24 @@ cudaEvent_t get_event(hlm_ctx* c) {
 }
 
 template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, hlm::rk45_window_kernel<Model, T>, 128, 0));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    // schedule: tiles (a warp stays with 32 consecutive links) or lane refill (rk45_window.cuh); by default
+    // lanes for routed runs, whose links take unlike numbers of attempts per launch, tiles otherwise
+    const bool lanes = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && c->routed);
+    static int blocks_per_sm[2] = {0, 0};
+    if (blocks_per_sm[lanes] == 0) {
+        if (lanes)
+            HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], hlm::rk45_lanes_kernel<Model, T>, 128, 0));
+        else
+            HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], hlm::rk45_window_kernel<Model, T>, 128, 0));
+        if (blocks_per_sm[lanes] < 1) blocks_per_sm[lanes] = 1;
     }
-    long long grid = std::min<long long>((a.n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm);
+    long long grid = std::min<long long>((a.n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm[lanes]);
     if (grid < 1) grid = 1;
     HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     HLM_CUDA(cudaEventRecord(e0, c->stream));
-    hlm::rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
+    if (lanes) hlm::rk45_lanes_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
+    else hlm::rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
     HLM_CUDA(cudaGetLastError());
     HLM_CUDA(cudaEventRecord(e1, c->stream));
     c->timing.emplace_back(e0, e1);
@@ -558,6 +567,13 @@ int hlm_set_dense_window_bytes(hlm_ctx* c, long long v) {
 int hlm_set_stiff_fallback(hlm_ctx* c, int enable) {
     HLM_REQUIRE(c, "hlm_set_stiff_fallback: ctx is NULL");
     c->stiff_fallback = enable != 0;
+    return HLM_OK;
+}
+
+int hlm_set_schedule(hlm_ctx* c, int mode) {
+    HLM_REQUIRE(c && (mode == HLM_SCHEDULE_AUTO || mode == HLM_SCHEDULE_TILES || mode == HLM_SCHEDULE_LANES),
+                "hlm_set_schedule: mode must be HLM_SCHEDULE_AUTO, _TILES or _LANES");
+    c->schedule = mode;
     return HLM_OK;
 }
 

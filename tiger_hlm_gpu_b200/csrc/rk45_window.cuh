@@ -234,6 +234,9 @@ __device__ __forceinline__ long long forcing_index(double t, double dt_min, long
     return idx;
 }
 
+// Tile schedule: a warp takes 32 consecutive links and stays with them until the slowest lane leaves.  Right
+// when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
+// threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
 template <class Model, typename T>
 __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
@@ -279,124 +282,11 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         int budget = (a.max_attempts > 0x7fffffffLL) ? 0x7fffffff : (int)a.max_attempts;
 
         for (;;) {
-            if (!(t < tf)) { status = kDone; break; }
-            if (!run_to_end && next_q >= a.q_hi) break;  // window complete for this link: pause
-            if (a.max_attempts > 0 && budget-- <= 0) { status = kStalled; break; }
-            if (f::add(t, h) > tf) h = f::sub(tf, t);  // rk45_kernel.cu:54
-
-            // ---- forcing sample at the step-start time, held for all stages ----
-            if (Model::N_FORC > 0 && a.n_forc > 0) {
-                const double td = (double)t;
-                if (!(td >= f_lo && td < f_hi)) {
-                    f_lo = -fp<double>::inf();
-                    f_hi = fp<double>::inf();
-#pragma unroll
-                    for (int j = 0; j < Model::N_FORC; ++j) {
-                        if (j < a.n_forc) {
-                            double lo, hi;
-                            const long long idx = forcing_index(td, a.forc_dt_min[j], a.forc_nT[j], lo, hi);
-                            // resident chunk of the record (the host checks that it covers the interval; the
-                            // clamp only keeps a mis-driven run inside the buffer)
-                            long long r = idx - a.forc_i0[j];
-                            r = r < 0 ? 0 : (r >= a.forc_nres[j] ? a.forc_nres[j] - 1 : r);
-                            const T v = (T)__ldg(a.forc[j] + r * a.forc_ncols + col);  // f32 -> f64 widening as model_204.hpp:82-83
-                            if (!f::same_bits(v, F[j])) k0_valid = false;
-                            F[j] = v;
-                            f_lo = fmax(f_lo, lo);
-                            f_hi = fmin(f_hi, hi);
-                        }
-                    }
-                }
-            }
-
-            // Fast attempt: constant-divisor divisions without guards, `bad` collects any operand that
-            // needs the real div.rn.f64; then (rarely) the attempt is redone with exact divisions.
-            // fac0 = safety * pow(1/(err + 1e-16), 0.2): the controller's factor, needed on both the
-            // accept and the reject branch (rk45_kernel.cu:151,156), so computed once here.
-            bool bad = !fast_ok, fsal = false;
-            T err, fac0;
-            if (!bad) {
-                if (!k0_valid) Model::template rhs<T, true>(y, F, L, k[0], bad);  // rk45_kernel.cu:114
-                err = dopri_attempt<Model, T, true>(y, k, h, F, L, rtol, atol, y_next, fsal, bad);
-                fac0 = f::mul(safety, f::template pow_pos<true>(f::template rcp_pos<true>(f::add(err, (T)1e-16), bad), (T)0.2, bad));
-            }
-            if (__builtin_expect(bad, 0)) {
-                bool unused = false;
-                Model::template rhs<T, false>(y, F, L, k[0], unused);
-                err = dopri_attempt<Model, T, false>(y, k, h, F, L, rtol, atol, y_next, fsal, unused);
-                fac0 = f::mul(safety, f::template pow_pos<false>(f::rcp(f::add(err, (T)1e-16)), (T)0.2, unused));
-            }
-
-            if (err <= (T)1) {
-                reject_run = 0;
-                // slope-jump detection, event_detector.cuh:46-53 + rk45_kernel.cu:132-136
-                T jump = (T)0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const T d = f::abs(f::sub(k[0][i], k[1][i]));
-                    if (d > jump) jump = d;
-                }
-                if (jump > (T)kSlopeJumpThresh) {
-                    h = f::max_a(h_floor, f::mul(h, (T)0.5));
-                    ++n_jmp;
-                    k0_valid = true;  // same t, y, F
-                    continue;
-                }
-                const T t1 = f::add(t, h);
-                // ---- dense output for queries in (t, t1], rk45_kernel.cu:139-148 ----
-                bool overshoot = false;
-                if (next_q < a.nq && tq_next <= t1) {
-                    // Q depends on the step only: built once here, not per query as the reference does.
-                    T Q[4][N];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m)
-#pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            T sum = (T)0;
-#pragma unroll
-                            for (int j = 0; j < 7; ++j) sum = f::fma(dp::tab<T>::get().P[j][m], k[j][i], sum);
-                            Q[m][i] = sum;
-                        }
-                    do {
-                        if (next_q >= a.q_hi) { overshoot = true; break; }
-                        if (tq_next > t && a.dense != nullptr) {
-                            const T th = f::div(f::sub(tq_next, t), h);
-                            double* out = a.dense + ((sys - a.dense_sys0) * qw + (next_q - a.q_lo)) * N;
-                            const T th2 = f::mul(th, th), th3 = f::mul(th2, th), th4 = f::mul(th3, th);
-#pragma unroll
-                            for (int i = 0; i < N; ++i) {
-                                T poly = f::fma(Q[0][i], th, (T)0);
-                                poly = f::fma(Q[1][i], th2, poly);
-                                poly = f::fma(Q[2][i], th3, poly);
-                                poly = f::fma(Q[3][i], th4, poly);
-                                out[i] = (double)f::fma(h, poly, y[i]);
-                            }
-                        }
-                        ++next_q;
-                        tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
-                    } while (next_q < a.nq && tq_next <= t1);
-                }
-                if (overshoot) break;  // step spans past this window's buffer: leave it uncommitted, redo next window
-
-                // FSAL (see dopri_attempt); the forcing sample must also be unchanged (checked next iteration)
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    y[i] = y_next[i];
-                    k[0][i] = k[6][i];
-                }
-                k0_valid = fsal;
-                t = t1;
-                ++n_acc;
-                h = f::mul(h, f::min_a(maxScale, f::max_a(minScale, fac0)));
-            } else {
-                ++reject_run;
-                ++n_rej;
-                T fac = f::min_a((T)1, fac0);
-                fac = f::min_a(maxScale, f::max_a(minScale, fac));
-                h = f::mul(h, fac);
-                k0_valid = true;  // same t, y, F
-                if (reject_run > 5 || h < h_stiff) { status = kStiff; break; }  // rk45_kernel.cu:160-162
-            }
+#define HLM_LEAVE break
+#define HLM_AGAIN continue
+#include "rk45_attempt_body.inc"
+#undef HLM_LEAVE
+#undef HLM_AGAIN
         }
         // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
         // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
@@ -419,6 +309,149 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
                 const int slot = __ldg(a.send_slot + sys);
                 if (slot >= 0) a.send_buf[slot] = (double)y[0];
             }
+        }
+    }
+}
+
+
+// Constants of one launch, shared by every link.
+template <typename T> struct RunConsts {
+    T rtol, atol, safety, minScale, maxScale, h_floor, h_stiff, tf;
+    bool run_to_end;
+    int qw;
+    __device__ __forceinline__ explicit RunConsts(const WindowArgs& a) {
+        using f = fp<T>;
+        rtol = (T)a.prm.rtol;
+        atol = (T)a.prm.atol;
+        safety = (T)a.prm.safety;
+        minScale = (T)a.prm.minScale;
+        maxScale = (T)a.prm.maxScale;
+        h_floor = f::mul((T)a.prm.initialStep, (T)kMinStepFraction);     // rk45_kernel.cu:134
+        h_stiff = f::mul(f::sub((T)a.tf, (T)a.t0), (T)kMinStepFraction);  // rk45_kernel.cu:160
+        tf = (T)a.tf;
+        run_to_end = (a.q_hi >= a.nq);
+        qw = a.q_hi - a.q_lo;
+    }
+};
+
+// One link's integration state, held in registers by its lane: load() / attempt() ... / store().
+// attempt() is one pass of the reference's loop body (rk45_kernel.cu:53-164) and returns true when the lane
+// leaves the link: integrated to tf, paused at the window's end, out of attempts, or flagged stiff.
+template <class Model, typename T> struct LinkRun {
+    using f = fp<T>;
+    static constexpr int N = Model::N_EQ;
+    long long sys, col;
+    T y[N], k[7][N], y_next[N];
+    T t, h, tq_next;
+    int next_q, reject_run, status, budget;
+    unsigned int n_acc, n_rej, n_jmp;
+    typename Model::template Link<T> L;
+    bool fast_ok, k0_valid;
+    T F[2];
+    double f_lo, f_hi;
+
+    // coalesced columns when the lanes of a warp hold consecutive links
+    __device__ __forceinline__ void load(const WindowArgs& a, long long sys_) {
+        sys = sys_;
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = (T)a.y[(long long)i * a.ld + sys];
+        t = (T)a.t[sys];
+        h = (T)a.h[sys];
+        next_q = a.next_q[sys];
+        reject_run = a.reject_run[sys];
+        n_acc = a.n_accept[sys];
+        n_rej = a.n_reject[sys];
+        n_jmp = a.n_jump[sys];
+        L.load(a.sp, a.ld, sys);
+        if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
+        fast_ok = Model::template fast_div_ok<T>(L);
+        col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
+        F[0] = F[1] = (T)0;
+        f_lo = fp<double>::inf();
+        f_hi = -fp<double>::inf();  // empty validity interval
+        tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
+        k0_valid = false;
+        budget = (a.max_attempts > 0x7fffffffLL) ? 0x7fffffff : (int)a.max_attempts;
+    }
+
+    __device__ __forceinline__ bool attempt(const WindowArgs& a, const RunConsts<T>& c) {
+        const T rtol = c.rtol, atol = c.atol, safety = c.safety, minScale = c.minScale, maxScale = c.maxScale;
+        const T h_floor = c.h_floor, h_stiff = c.h_stiff, tf = c.tf;
+        const bool run_to_end = c.run_to_end;
+        const int qw = c.qw;
+#define HLM_LEAVE return true
+#define HLM_AGAIN return false
+#include "rk45_attempt_body.inc"
+#undef HLM_LEAVE
+#undef HLM_AGAIN
+        return false;
+    }
+
+    // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
+    // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
+    __device__ __forceinline__ void store(const WindowArgs& a) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.y[(long long)i * a.ld + sys] = (double)y[i];
+        a.t[sys] = (double)t;
+        a.h[sys] = (double)h;
+        a.next_q[sys] = next_q;
+        a.reject_run[sys] = reject_run;
+        a.status[sys] = status;
+        a.n_accept[sys] = n_acc;
+        a.n_reject[sys] = n_rej;
+        a.n_jump[sys] = n_jmp;
+        // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
+        // links need for the next interval goes straight into the send buffer
+        if constexpr (Model::HAS_INFLOW) {
+            if (a.send_slot != nullptr && status != kActive) {
+                const int slot = __ldg(a.send_slot + sys);
+                if (slot >= 0) a.send_buf[slot] = (double)y[0];
+            }
+        }
+    }
+};
+
+// Lane-refill schedule: every lane owns one link at a time and, the moment it leaves it, takes the next
+// unclaimed link of the launch (warp-aggregated claim: one atomicAdd per warp and iteration, ranks by ballot),
+// so a warp never idles behind its slowest link.  For workloads whose links take unlike numbers of attempts
+// per launch — routed runs: short coupling intervals, discharge growing downstream, 3 attempts on average
+// and 20 at the tail — where the tile schedule leaves three quarters of the lanes idle.  Loads and stores of a
+// lane are then its own (not coalesced): per link that is ~300 bytes against thousands of FP64 instructions.
+// Per-link arithmetic is the same function, so results are bit-identical under either schedule.
+template <class Model, typename T>
+__global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_lanes_kernel(const WindowArgs a) {
+    const unsigned int lane = threadIdx.x & 31;
+    const long long first = a.tile_lo << 5;
+    const long long last = ((a.tile_lo + a.n_tiles) << 5) < a.ns ? ((a.tile_lo + a.n_tiles) << 5) : a.ns;
+    const long long n_links = last - first;
+    const RunConsts<T> c(a);
+    LinkRun<Model, T> r;
+    bool have = false, exhausted = false;
+    for (;;) {
+        const unsigned int need = __ballot_sync(0xffffffffu, !have && !exhausted);
+        if (need) {
+            unsigned int base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.tile_counter, (unsigned int)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have && !exhausted) {
+                const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (idx >= n_links) {
+                    exhausted = true;
+                } else if (a.status[first + idx] == kActive) {
+                    r.status = kActive;
+                    r.load(a, first + idx);
+                    have = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, have) == 0u) {
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            continue;
+        }
+        if (have && r.attempt(a, c)) {
+            r.store(a);
+            have = false;
         }
     }
 }
