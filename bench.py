@@ -124,7 +124,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: timed region shorter than the 200 ms sampling period"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
                 "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -559,6 +559,22 @@ def main():
         except Exception as ex:
             ref_cuda = {"error": repr(ex)}
 
+    notebook = None
+    if rank == 0 and world == 1 and not args.no_baselines:
+        # the reference's CPU path as the north star names it: the notebook's SciPy integrator, one process per core
+        try:
+            from oracle import notebook_baseline as NB
+            cores = os.cpu_count() or 1
+            ns_nb = 24 * cores
+            sp_n, col_n, pr_n, t2m_n, y0_n, tq_n = cpu_sample_inputs(ns_nb, args)
+            _, steps_nb, dt_nb, procs = NB.run(sp_n, pr_n, t2m_n, col_n, y0_n, 0.0, DAY, tq_n[1:], processes=cores)
+            notebook = {"value": steps_nb / dt_nb, "unit": "accepted system-steps/s", "cores": procs, "kind": "reference",
+                        "sample": f"scipy.integrate.solve_ivp(method='RK45', rtol=1e-6, atol=1e-9, t_eval=hourly) per link as "
+                                  f"model_dummy_python.ipynb:150-175,935-945 does, {ns_nb} links x 1 simulated day of the bench "
+                                  f"workload, {steps_nb} accepted steps in {dt_nb:.2f} s wall on {procs} processes"}
+        except Exception as ex:
+            notebook = {"error": repr(ex)}
+
     if rank == 0:
         hbm_peak, hbm_src = peaks()
         kern_avg_ms = kern_ms_all / max(kern_n_all, 1)
@@ -589,7 +605,7 @@ def main():
                          "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_window_kernel<Model204,double>",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_link_per_launch": bytes_per_link}},
-            "cpu_baseline": cpu, "reference_cuda": ref_cuda, "clocks": clocks, "host_binding": numa,
+            "cpu_baseline": cpu, "notebook_cpu": notebook, "reference_cuda": ref_cuda, "clocks": clocks, "host_binding": numa,
         }
         print(json.dumps(line), flush=True)
     solver.close()
