@@ -204,3 +204,46 @@ def test_driver_reports_errors_like_main(tmp_path):
     subprocess.check_call(["make", "-C", HOST, "build/hlm_run"], stdout=subprocess.DEVNULL)
     out = subprocess.run([RUN, str(tmp_path / "bad.yaml")], capture_output=True, text=True, timeout=120)
     assert out.returncode == 1 and "nope" in out.stderr
+
+
+def test_driver_routed_model200(tmp_path):
+    """routing.enabled: Model 200 links coupled along next_stream (here one chain of 203 links), coupling
+    interval 30 min, implicit fallback on; against the Python mirror's RoutedSolver, bit for bit."""
+    from tiger_hlm_gpu_b200 import routing
+    pr, t2m, col = write_case(tmp_path)
+    cfg = config_text("2021-01-01T00:00:00", "2021-01-02T00:00:00", states="[0, 1, 2, 3, 4]", prefix="r_")
+    cfg = cfg.replace("uid: 204", "uid: 200").replace("name: Model204", "name: Model200")
+    cfg += 'routing:\n  enabled: true\n  couple: "30m"\n  subbasin_links: 64\n'
+    (tmp_path / "routed.yaml").write_text(cfg)
+    run_driver(tmp_path, "routed.yaml")
+    fin, den = read_nc(tmp_path / "out" / "r_final_rank_0.nc"), read_nc(tmp_path / "out" / "r_dense_rank_0.nc")
+    sp = hostio.load_spatial_params(str(tmp_path / "params" / "links.csv"))
+    p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=64)
+    y0 = np.tile([0.5, 3.0, 0.0, 5.0, 0.2], (NS, 1))
+    tq_all = 60.0 * np.arange(25)
+    dense = np.zeros((NS, 25, 5))
+    with hlm.Solver(0) as s:
+        s.set_model_parameters(200, hlm.Parameters(initialStep=1e-6))
+        s.set_max_attempts(2_000_000)
+        s.upload_spatial_params(sp)
+        s.upload_forcing(0, 1.0, pr)
+        s.upload_forcing(1, 24.0, t2m)
+        s.set_forcing_columns(col)
+        rs = routing.RoutedSolver(s, 200, p1.ranks[0], 1, 0)
+        for k in range(48):
+            ta, tb = 30.0 * k, 30.0 * (k + 1)
+            sel = np.flatnonzero((tq_all > ta) & (tq_all <= tb)) if k else np.flatnonzero(tq_all <= tb)
+            tq = tq_all[sel]
+            if k == 0:
+                rs.begin(y0, ta, tb, tq)
+            rs.advance(tb, tq)
+            if len(tq):
+                win = np.zeros((NS, len(tq), 5))
+                s.solve_wait_copy(s.solve_fetch_window_packed(win))
+                dense[:, sel] = win
+        r = rs.end()
+    assert np.isin(r["stiff"], (0, 3)).all()
+    assert np.array_equal(fin["outputs"], r["final"])
+    assert np.array_equal(den["outputs"], dense)
+    q = r["final"][:, 0]
+XX

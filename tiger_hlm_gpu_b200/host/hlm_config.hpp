@@ -14,6 +14,9 @@
 //   output.dir / output.prefix / output.format (netcdf|csv) / output.dense (bool)
 //   solver.interval: "1d"      the run is driven in intervals of this length
 //   solver.max_attempts        per-link attempt budget per window (0 = unbounded like the reference)
+//   solver.stiff_fallback: true   links the RK45 path flags stiff are continued by the Radau IIA fallback
+//   routing: {enabled: true, couple: "15m"}   links coupled through next_stream (Model 200): the run advances
+//                              in coupling intervals, upstream discharge held over each
 #pragma once
 
 #include <chrono>
@@ -260,7 +263,9 @@ struct SimulationConfig {
         bool override_initial_step = false;
         std::string interval = "1d";
         long long max_attempts = 0;
+        bool stiff_fallback = false;
     } solver;
+    struct RoutingInfo { bool enabled = false; std::string couple = "15m"; long long subbasin_links = 4096; } routing;
     struct MPIInfo { int step_storage = 0, transfer_buffer = 0, discontinuity_buf = 0; } mpi;
     struct FlagsInfo { bool uses_dam = false, convert_area = false; } flags;
 };
@@ -368,6 +373,13 @@ inline SimulationConfig config_from_yaml(const hlmyaml::Node& doc) {
     }
     cfg.solver.interval = s["interval"].as_string_or("1d");
     if (s["max_attempts"]) cfg.solver.max_attempts = s["max_attempts"].as_int("solver.max_attempts");
+    if (s["stiff_fallback"]) cfg.solver.stiff_fallback = s["stiff_fallback"].as_bool("solver.stiff_fallback");
+    if (doc["routing"]) {
+        const Node& r = doc["routing"];
+        if (r["enabled"]) cfg.routing.enabled = r["enabled"].as_bool("routing.enabled");
+        cfg.routing.couple = r["couple"].as_string_or("15m");
+        if (r["subbasin_links"]) cfg.routing.subbasin_links = r["subbasin_links"].as_int("routing.subbasin_links");
+    }
     // 9) mpi (required by the reference's loader; optional here: no MPI on this path)
     if (doc["mpi"]) {
         const Node& mp = doc["mpi"];

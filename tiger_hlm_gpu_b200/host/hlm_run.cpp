@@ -26,6 +26,7 @@
 
 #include "hlm_config.hpp"
 #include "hlm_host.hpp"
+#include "hlm_routing.hpp"
 #include "hlm_netcdf.hpp"
 
 namespace {
@@ -104,8 +105,9 @@ std::vector<double> initial_states(const SimulationConfig& cfg, const std::strin
     t_start_minutes = 0.0;
     if (cfg.initial.mode == "cold") {
         const double common204[5] = {0.01, 3.0, 0.0, 5.0, 0.2};
+        const double common200[5] = {0.5, 3.0, 0.0, 5.0, 0.2};  // channel discharge 0.5 m3/s + Model204's stores
         for (size_t s = 0; s < ns; ++s)
-            for (int i = 0; i < n_eq; ++i) y0[s * n_eq + i] = (cfg.model.uid == 204 && i < 5) ? common204[i] : 1.0;
+            for (int i = 0; i < n_eq; ++i) y0[s * n_eq + i] = (cfg.model.uid == 204 && i < 5) ? common204[i] : ((cfg.model.uid == 200 && i < 5) ? common200[i] : 1.0);
         return y0;
     }
     if (cfg.initial.mode != "hot") throw std::runtime_error("initial.mode must be 'cold' or 'hot'");
@@ -248,7 +250,26 @@ int run(const Options& opt) {
     const double dq = parse_interval_minutes(cfg.output.print_interval);
     std::vector<double> tq;
     for (double t = t_begin; t <= t_end; t += dq) tq.push_back(t);  // main.cpp:653-657
-    const double interval = parse_interval_minutes(cfg.solver.interval);
+    // routed run: the interval is the coupling interval and every link continues across it (hlm_solve_advance)
+    const bool routed = cfg.routing.enabled;
+    if (routed) {
+        if (opt.world != 1)
+            throw std::runtime_error("routing: this driver runs routed networks on one rank; a multi-rank run needs the host's "
+                                     "collective between intervals (hlm_b200::RoutedRun, INTEGRATION.md section 6)");
+        std::vector<long long> stream((size_t)ns), next((size_t)ns);
+        for (long long s = 0; s < ns; ++s) {
+            stream[(size_t)s] = sp[(size_t)s].stream;
+            next[(size_t)s] = sp[(size_t)s].next_stream;
+        }
+        const hlm_b200::RoutePlan plan = hlm_b200::plan_routes(stream, next, 1, cfg.routing.subbasin_links);
+        const hlm_b200::RankTopology& tp = plan.ranks[0];
+        check(hlm_route_set_topology(ctx, tp.up_ptr.data(), tp.up_idx.empty() ? nullptr : tp.up_idx.data(), ns, nullptr, 0),
+              "hlm_route_set_topology");
+        say("routing: " + std::to_string(tp.up_idx.size()) + " links drain into another link, " + std::to_string(plan.n_subbasins) +
+            " sub-basins, coupling interval " + cfg.routing.couple);
+    }
+    check(hlm_set_stiff_fallback(ctx, (cfg.solver.stiff_fallback || routed) ? 1 : 0), "hlm_set_stiff_fallback");
+    const double interval = parse_interval_minutes(routed ? cfg.routing.couple : cfg.solver.interval);
     const double chunk = std::max(interval, parse_interval_minutes("30d"));
 
     std::vector<int> states = cfg.output.states;
@@ -299,7 +320,11 @@ int run(const Options& opt) {
         const long long nq = (long long)(q_end - q_next);
         upload_forcing_for(ta, tb);
         if (first) check(hlm_solve_begin(ctx, cfg.model.uid, y0.data(), ns, ta, tb, tq.data() + q_next, nq), "hlm_solve_begin");
-        else check(hlm_solve_restart(ctx, ta, tb, tq.data() + q_next, nq), "hlm_solve_restart");
+        if (routed) check(hlm_route_gather(ctx, nullptr), "hlm_route_gather");  // inflow of this interval from the state at its start
+        if (!first) {
+            if (routed) check(hlm_solve_advance(ctx, tb, tq.data() + q_next, nq), "hlm_solve_advance");
+            else check(hlm_solve_restart(ctx, ta, tb, tq.data() + q_next, nq), "hlm_solve_restart");
+        }
         first = false;
         const bool want_dense = cfg.output.dense && nq > 0;
         for (long long q = 0;;) {
@@ -348,16 +373,17 @@ int run(const Options& opt) {
         write_final_netcdf(out_dir + "/" + cfg.output.prefix + "final" + suffix + ".nc", y_final.data(), linkids.data(), all_states.data(), (int)ns, n_eq, 0);
         if (dense_writer) dense_writer->close();
     }
-    long long acc = 0, rej = 0, jump = 0, stiff = 0, stalled = 0;
+    long long acc = 0, rej = 0, jump = 0, stiff = 0, stalled = 0, solved = 0;
     for (long long s = 0; s < ns; ++s) {
         acc += n_acc[s]; rej += n_rej[s]; jump += n_jump[s];
         stiff += code[s] == HLM_LINK_STIFF;
+        solved += code[s] == HLM_LINK_STIFF_SOLVED;
         stalled += code[s] == HLM_LINK_STALLED;
     }
     const double wall_s = std::chrono::duration<double>(clock::now() - wall0).count();
     std::printf("[rank %d] done: %lld links, %zu queries, t %.1f -> %.1f min; accepted %lld rejected %lld slope-jump %lld; "
-                "stiff %lld stalled %lld; solve %.3f s (%.3e accepted steps/s), total %.3f s\n",
-                opt.rank, ns, tq.size(), t_begin, t_end, acc, rej, jump, stiff, stalled, solve_s, acc / std::max(solve_s, 1e-9), wall_s);
+                "stiff %lld (+%lld finished implicitly) stalled %lld; solve %.3f s (%.3e accepted steps/s), total %.3f s\n",
+                opt.rank, ns, tq.size(), t_begin, t_end, acc, rej, jump, stiff, solved, stalled, solve_s, acc / std::max(solve_s, 1e-9), wall_s);
     return 0;
 }
 
