@@ -246,4 +246,4 @@ def test_driver_routed_model200(tmp_path):
     assert np.array_equal(fin["outputs"], r["final"])
     assert np.array_equal(den["outputs"], dense)
     q = r["final"][:, 0]
-XX
+    assert q[-1] > 20 * q[0]                     # the chain outlet carries the discharge of everything above it
