@@ -185,3 +185,21 @@ def test_three_ranks_with_a_simulated_exchange_equal_one_rank_bit_for_bit():
         final3[p3.order[topo.lo:topo.hi]] = rk.y
         na3[p3.order[topo.lo:topo.hi]] = rk.na
     assert np.array_equal(final3, final1) and np.array_equal(dense3, dense1) and np.array_equal(na3, na1)
+
+
+def test_model200_regression_fixture():
+    """tests/golden/model200_routed.npz (written by tests/golden/make_model200_golden.py): the oracle with the
+    restated libdevice pow reproduces it bit for bit — a self-pin over time, Model 200 has no reference counterpart."""
+    import os
+    from tests.golden.make_model200_golden import case
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model200_routed.npz"))
+    sp, col, pr, t2m, y0 = case()
+    F = O.Forcing([pr, t2m], [1.0, 24.0], col=col)
+    un = O.run_rk45(200, PRM, y0, 0.0, 720.0, 60.0 * np.arange(1, 13), sp=sp, forcing=F, device_pow=True, max_attempts=1_000_000)
+    for k in ("final", "dense", "n_accept", "n_reject", "stiff"):
+        assert np.array_equal(un[k], g["unrouted_" + k]), k
+    p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=12)
+    fin, dense, tqr, na = routed_ref.run_single(sp, F, y0, PRM, p1, 0.0, 360.0, 20.0, threads=2)
+    assert np.array_equal(fin, g["routed_final"]) and np.array_equal(dense, g["routed_dense"])
+    assert np.array_equal(tqr, g["routed_tq"]) and np.array_equal(na, g["routed_n_accept"])
+    assert (g["unrouted_dense"][:, :, 2] > 0).any()      # some links pond water: both pow() call sites are covered
