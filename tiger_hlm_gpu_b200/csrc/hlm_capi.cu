@@ -89,6 +89,9 @@ struct hlm_ctx {
     cudaStream_t own_stream = nullptr;   // compute
     cudaStream_t stream = nullptr;       // = own_stream or the caller's
     cudaStream_t copy_stream = nullptr;  // D2H of finished windows
+    cudaStream_t h2d_stream = nullptr;   // y0 of later chunks while the first ones integrate (run_link_chunks)
+    DevBuf<double> io_stage;             // y0 in, results out, in the caller's layouts
+    std::vector<cudaEvent_t> chunk_ready;
     std::map<int, hlm::SolverParams> params;
     long long max_attempts = 0;
     long long dense_window_bytes = 8LL << 30;
@@ -179,12 +182,14 @@ __global__ void prepare_params_kernel(const unsigned char* __restrict__ aos, lon
     for (int c = 0; c < Model::N_SP; ++c) soa[(long long)c * ld + i] = out[c];
 }
 
+// links [lo, hi) of the padded range (hi may reach ld: padding lanes are parked as done)
 __global__ void init_state_kernel(const double* __restrict__ y0_aos, int n_eq, long long ns, long long ld,
                                   double* __restrict__ y, double* __restrict__ t, double* __restrict__ h,
                                   int* next_q, int* reject_run, int* status, unsigned int* n_acc,
-                                  unsigned int* n_rej, unsigned int* n_jump, double t0, double h0) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ld) return;
+                                  unsigned int* n_rej, unsigned int* n_jump, double t0, double h0, long long lo,
+                                  long long hi) {
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
     const bool live = i < ns;
     for (int c = 0; c < n_eq; ++c) y[(long long)c * ld + i] = live ? y0_aos[i * n_eq + c] : 0.0;
     t[i] = t0;
@@ -219,9 +224,9 @@ __global__ void export_results_kernel(const double* __restrict__ y, const int* _
                                       const unsigned int* __restrict__ n_acc, const unsigned int* __restrict__ n_rej,
                                       const unsigned int* __restrict__ n_jump, int n_eq, long long ns, long long ld,
                                       double* __restrict__ out_aos, long long* __restrict__ out_cnt,
-                                      int* __restrict__ out_code) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ns) return;
+                                      int* __restrict__ out_code, long long lo, long long hi) {
+    long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
     const int s = status[i];
     const bool ok = s == hlm::kDone || s == hlm::kDoneStiff;
     if (out_aos)
@@ -414,6 +419,7 @@ int hlm_create(int device, hlm_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_kernel_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming);
@@ -446,6 +452,8 @@ void hlm_destroy(hlm_ctx* c) {
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    for (cudaEvent_t ev : c->chunk_ready) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -605,8 +613,17 @@ int hlm_kernel_time_ms(hlm_ctx* c, double* sum_ms, long long* n) {
 
 // ---- session ------------------------------------------------------------------------------------
 
+static int solve_begin_impl(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
+                            long long nq, bool defer_state);
+
 int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
                     long long nq) {
+    return solve_begin_impl(c, uid, y0, ns, t0, tf, tq, nq, false);
+}
+
+// defer_state: the caller uploads y0 and initialises the state itself, chunk by chunk (run_link_chunks)
+static int solve_begin_impl(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
+                            long long nq, bool defer_state) {
     HLM_REQUIRE(c, "hlm_solve_begin: ctx is NULL");
     const ModelInfo* m = find_model(uid);
     if (!m) return fail(HLM_ERR_INVALID, "hlm_solve_begin: unknown model uid " + std::to_string(uid));
@@ -650,16 +667,18 @@ int hlm_solve_begin(hlm_ctx* c, int uid, const double* y0, long long ns, double 
     HLM_CUDA(cudaMemsetAsync(c->n_radau.p, 0, sizeof(unsigned int) * ld, c->stream));
     HLM_CUDA(c->tq.reserve((size_t)std::max<long long>(nq, 1)));
     if (nq > 0) HLM_CUDA(cudaMemcpyAsync(c->tq.p, tq, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, c->stream));
-    // y0 arrives [link][state]; stage it in the (not yet used) dense buffer, then transpose to columns
-    HLM_CUDA(c->dense[0].reserve((size_t)ns * m->n_eq));
-    HLM_CUDA(cudaMemcpyAsync(c->dense[0].p, y0, sizeof(double) * (size_t)ns * m->n_eq, cudaMemcpyHostToDevice, c->stream));
-    const hlm::SolverParams& prm = c->params[uid];
-    const int tpb = 256;
-    init_state_kernel<<<(unsigned)((c->ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
-        c->dense[0].p, m->n_eq, ns, c->ld, c->y.p, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p,
-        c->n_acc.p, c->n_rej.p, c->n_jump.p, t0, prm.initialStep);
-    HLM_CUDA(cudaGetLastError());
-    ++c->launches;
+    if (!defer_state) {
+        // y0 arrives [link][state]; stage it in the (not yet used) dense buffer, then transpose to columns
+        HLM_CUDA(c->dense[0].reserve((size_t)ns * m->n_eq));
+        HLM_CUDA(cudaMemcpyAsync(c->dense[0].p, y0, sizeof(double) * (size_t)ns * m->n_eq, cudaMemcpyHostToDevice, c->stream));
+        const hlm::SolverParams& prm = c->params[uid];
+        const int tpb = 256;
+        init_state_kernel<<<(unsigned)((c->ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+            c->dense[0].p, m->n_eq, ns, c->ld, c->y.p, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p,
+            c->n_acc.p, c->n_rej.p, c->n_jump.p, t0, prm.initialStep, 0, c->ld);
+        HLM_CUDA(cudaGetLastError());
+        ++c->launches;
+    }
     int r = 0;
     if (uid == hlm::Model204::UID) r = prepare_params<hlm::Model204>(c);
     if (uid == hlm::Model200::UID) r = prepare_params<hlm::Model200>(c);
@@ -924,7 +943,7 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
         const int tpb = 256;
         export_results_kernel<<<(unsigned)((ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(
             c->y.p, c->status.p, c->n_acc.p, c->n_rej.p, c->n_jump.p, c->n_eq, ns, c->ld, out_final ? d_final : nullptr, d_cnt,
-            d_code);
+            d_code, 0, ns);
         HLM_CUDA(cudaGetLastError());
         ++c->launches;
         if (out_final) HLM_CUDA(cudaMemcpyAsync(out_final, d_final, sizeof(double) * n_final, cudaMemcpyDeviceToHost, c->stream));
@@ -945,70 +964,133 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
 // of the caller's [link][query][state] array, so every device-to-host copy is a plain memcpy at full link
 // rate (windows over queries leave as 2-D copies of short rows), and it overlaps the next chunk's integration
 // (two buffers, copy stream).  Chunks shrink towards the end: what stays exposed is the copy of a small last one.
-static int run_link_chunks(hlm_ctx* c, double* out_dense) {
+// The state travels the same way: y0 of chunk i is uploaded (a third stream; PCIe is full duplex) and
+// initialised while earlier chunks integrate, and a chunk's final states, counters and codes are exported and
+// copied out right behind its dense records — so the call never waits for a whole-array transfer.
+static int run_link_chunks(hlm_ctx* c, const double* y0, double* out_dense, double* out_final, int* out_stiff,
+                           long long* out_acc, long long* out_rej, long long* out_jump) {
     const long long ns = c->ns, nq = c->nq;
-    const long long per_link = nq * c->n_eq * (long long)sizeof(double);
+    const int n_eq = c->n_eq;
+    const long long per_link = nq * n_eq * (long long)sizeof(double);
     const long long n_tiles_all = (ns + 31) / 32;
     const long long tiles_max = std::max<long long>(1, c->dense_window_bytes / (per_link * 32));
-    long long n_chunks = std::max<long long>((n_tiles_all + tiles_max - 1) / tiles_max, std::min<long long>(8, n_tiles_all));
+    const long long n_chunks = std::max<long long>((n_tiles_all + tiles_max - 1) / tiles_max, std::min<long long>(8, n_tiles_all));
     if (int r = check_forcing_cover(c)) return r;
-    const double total_w = 0.5 * (double)n_chunks * (double)(n_chunks + 1);
-    double acc_w = 0.0;
-    long long tile = 0;
-    for (long long i = 0; tile < n_tiles_all; ++i) {
-        acc_w += (double)std::max<long long>(n_chunks - i, 1);
-        long long end = (long long)std::llround((double)n_tiles_all * std::min(1.0, acc_w / total_w));
-        end = std::min(n_tiles_all, std::max(end, tile + 1));
-        end = std::min(end, tile + tiles_max);
+    std::vector<long long> ends;  // chunk i = tiles [ends[i-1], ends[i])
+    {
+        const double total_w = 0.5 * (double)n_chunks * (double)(n_chunks + 1);
+        double acc_w = 0.0;
+        long long tile = 0;
+        for (long long i = 0; tile < n_tiles_all; ++i) {
+            acc_w += (double)std::max<long long>(n_chunks - i, 1);
+            long long end = (long long)std::llround((double)n_tiles_all * std::min(1.0, acc_w / total_w));
+            end = std::min(n_tiles_all, std::max(end, tile + 1));
+            end = std::min(end, tile + tiles_max);
+            ends.push_back(end);
+            tile = end;
+        }
+    }
+    // staging in the caller's layouts: [ns][n_eq] doubles (y0 in, final states out), 3 x [ns] i64, [ns] i32
+    const size_t n_state = (size_t)ns * n_eq;
+    HLM_CUDA(c->io_stage.reserve(n_state + 3 * (size_t)ns + (size_t)ns / 2 + 1));
+    double* d_state = c->io_stage.p;
+    long long* d_cnt = reinterpret_cast<long long*>(d_state + n_state);
+    int* d_code = reinterpret_cast<int*>(d_cnt + 3 * (size_t)ns);
+    while (c->chunk_ready.size() < ends.size()) {
+        cudaEvent_t ev;
+        HLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->chunk_ready.push_back(ev);
+    }
+    const hlm::SolverParams& prm = c->params[c->uid];
+    const int tpb = 256;
+    // every upload is queued now, in chunk order, on its own stream
+    for (size_t i = 0; i < ends.size(); ++i) {
+        const long long lo = (i ? ends[i - 1] : 0) * 32, hi = std::min(ns, ends[i] * 32);
+        const long long hi_pad = (i + 1 == ends.size()) ? c->ld : hi;  // the last chunk parks the padding lanes
+        HLM_CUDA(cudaMemcpyAsync(d_state + (size_t)lo * n_eq, y0 + (size_t)lo * n_eq, sizeof(double) * (size_t)(hi - lo) * n_eq,
+                                 cudaMemcpyHostToDevice, c->h2d_stream));
+        init_state_kernel<<<(unsigned)((hi_pad - lo + tpb - 1) / tpb), tpb, 0, c->h2d_stream>>>(
+            d_state, n_eq, ns, c->ld, c->y.p, c->t.p, c->h.p, c->next_q.p, c->reject_run.p, c->status.p, c->n_acc.p, c->n_rej.p,
+            c->n_jump.p, c->t0, prm.initialStep, lo, hi_pad);
+        HLM_CUDA(cudaGetLastError());
+        ++c->launches;
+        HLM_CUDA(cudaEventRecord(c->chunk_ready[i], c->h2d_stream));
+    }
+    for (size_t i = 0; i < ends.size(); ++i) {
+        const long long tile = i ? ends[i - 1] : 0, end = ends[i];
         const long long lo = tile * 32, hi = std::min(ns, end * 32);
         const int buf = c->dense_cur ^ 1;
         if (c->copy_pending[buf]) {
             HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
             c->copy_pending[buf] = false;
         }
-        const size_t elems = (size_t)(hi - lo) * (size_t)nq * (size_t)c->n_eq;
+        const size_t elems = (size_t)(hi - lo) * (size_t)nq * (size_t)n_eq;
         HLM_CUDA(c->dense[buf].reserve(elems));
         HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
         c->dense_cur = buf;
+        HLM_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
         if (int r = queue_window(c, 0, nq, c->dense[buf].p, tile, end - tile, lo)) return r;
+        export_results_kernel<<<(unsigned)((hi - lo + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+            c->y.p, c->status.p, c->n_acc.p, c->n_rej.p, c->n_jump.p, n_eq, ns, c->ld, out_final ? d_state : nullptr, d_cnt, d_code,
+            lo, hi);
+        HLM_CUDA(cudaGetLastError());
+        ++c->launches;
         HLM_CUDA(cudaEventRecord(c->ev_kernel_done[buf], c->stream));
         HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
-        HLM_CUDA(cudaMemcpyAsync(out_dense + (size_t)lo * nq * c->n_eq, c->dense[buf].p, elems * sizeof(double),
+        HLM_CUDA(cudaMemcpyAsync(out_dense + (size_t)lo * nq * n_eq, c->dense[buf].p, elems * sizeof(double),
                                  cudaMemcpyDeviceToHost, c->copy_stream));
+        const size_t n = (size_t)(hi - lo);
+        if (out_final)
+            HLM_CUDA(cudaMemcpyAsync(out_final + (size_t)lo * n_eq, d_state + (size_t)lo * n_eq, sizeof(double) * n * n_eq,
+                                     cudaMemcpyDeviceToHost, c->copy_stream));
+        long long* outs[3] = {out_acc, out_rej, out_jump};
+        for (int k = 0; k < 3; ++k)
+            if (outs[k])
+                HLM_CUDA(cudaMemcpyAsync(outs[k] + lo, d_cnt + (size_t)k * ns + lo, sizeof(long long) * n, cudaMemcpyDeviceToHost,
+                                         c->copy_stream));
+        if (out_stiff) HLM_CUDA(cudaMemcpyAsync(out_stiff + lo, d_code + lo, sizeof(int) * n, cudaMemcpyDeviceToHost, c->copy_stream));
         HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
         c->copy_pending[buf] = true;
-        tile = end;
     }
     c->q_done = nq;
     c->win_q_lo = 0;
     c->win_q_hi = nq;
     c->win_has_dense = false;  // the buffers hold chunks of links, not a window a caller could fetch
+    HLM_CUDA(cudaStreamSynchronize(c->h2d_stream));
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    c->copy_pending[0] = c->copy_pending[1] = false;
     return HLM_OK;
 }
 
 int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
                  long long nq, double* out_final, double* out_dense, int* out_stiff, long long* out_acc,
                  long long* out_rej, long long* out_jump) {
+    HLM_REQUIRE(c, "hlm_run_rk45: ctx is NULL");
     if (!out_dense) nq = 0;  // nothing to emit: one window straight to tf
-    if (int r = hlm_solve_begin(c, uid, y0, ns, t0, tf, tq, nq)) return r;
+    // a large output leaves in chunks of links (run_link_chunks), which also pipelines the state in and out
+    bool chunked = false;
+    if (const ModelInfo* m = find_model(uid)) {
+        const long long per_q = ns * m->n_eq * (long long)sizeof(double);
+        const long long per_link = nq * m->n_eq * (long long)sizeof(double);
+        chunked = nq > 0 && ns > 0 && per_q * nq > std::min<long long>(256LL << 20, c->dense_window_bytes) &&
+                  per_link * 32 <= c->dense_window_bytes;
+    }
+    if (int r = solve_begin_impl(c, uid, y0, ns, t0, tf, tq, nq, chunked)) return r;
+    if (chunked) return run_link_chunks(c, y0, out_dense, out_final, out_stiff, out_acc, out_rej, out_jump);
     if (nq == 0) {
         if (int r = hlm_solve_window(c, 0, 0)) return r;
     } else {
+        // small output (one window), or a query list so long that even 32 links of it exceed a buffer:
+        // windows over queries
         const long long per_q = ns * c->n_eq * (long long)sizeof(double);
-        const long long per_link = nq * c->n_eq * (long long)sizeof(double);
-        if (per_q * nq > std::min<long long>(256LL << 20, c->dense_window_bytes) && per_link * 32 <= c->dense_window_bytes) {
-            if (int r = run_link_chunks(c, out_dense)) return r;
-        } else {
-            // small output (one window), or a query list so long that even 32 links of it exceed a buffer:
-            // windows over queries
-            const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
-            const long long n_win = (nq + qw_max - 1) / qw_max;
-            const long long qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
-            for (long long q = 0; q < nq;) {
-                q = std::min(nq, q + qw);
-                if (int r = hlm_solve_window(c, q, 1)) return r;
-                if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
-            }
+        const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
+        const long long n_win = (nq + qw_max - 1) / qw_max;
+        const long long qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver
+        for (long long q = 0; q < nq;) {
+            q = std::min(nq, q + qw);
+            if (int r = hlm_solve_window(c, q, 1)) return r;
+            if (int r = hlm_solve_fetch_window(c, out_dense)) return r;
         }
     }
     return hlm_solve_end(c, out_final, out_stiff, out_acc, out_rej, out_jump);
