@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-DRAM_BYTES_PER_LINK_PER_LAUNCH = 1348.3  # ncu: (263.83 MB read + 1084.46 MB write) / 1 M links, profiles/r1f_*
+DRAM_BYTES_PER_LINK_PER_LAUNCH = 1396.0  # ncu --set full of `python bench.py`: (2.642 GB read + 11.318 GB write) / 10 M links, profiles/r1h_*
 W_MIN_FLOP_PER_ATTEMPT = 561.0  # minimal-algorithm nominal FP64 flop per attempted Model204 step
 PRM6 = [1e-6, 1e-6, 1e-9, 0.9, 0.2, 10.0]  # initialStep (main.cpp:633-640), rtol, atol, safety, min/maxScale
 DAY = 1440.0
@@ -596,9 +596,9 @@ def main():
                          "achieved": achieved_tflops, "peak": fp_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
-                         # (profiles/r1f_ncu_full_window_kernel.csv: 1 M links, 24 queries), per link, times this launch's links
+                         # (profiles/r1h_ncu_full_window_kernel_10M.csv: this command, 10 M links, 24 queries), per link
                          "traffic": (DRAM_BYTES_PER_LINK_PER_LAUNCH * ns if args.precision == 64 and args.wet_fraction == 0.0 else None),
-                         "traffic_source": "ncu capture at 1 M links (profiles/r1f_ncu_full_window_kernel.csv), scaled per link",
+                         "traffic_source": "ncu --set full capture of this command (profiles/r1h_ncu_full_window_kernel_10M.csv), per link x links",
                          "peak_source": "measured live: register-resident FMA microbenchmark (hlm_measure_fma_peak); "
                                         "MEASURED_PEAKS.json holds no FP64/FP32 vector peak",
                          "flop_per_attempt": W_MIN_FLOP_PER_ATTEMPT, "attempts_per_launch": att_per_launch,

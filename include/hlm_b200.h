@@ -239,8 +239,9 @@ int hlm_route_send_buffer(hlm_ctx* ctx, void** dev_ptr, long long* n_send);
 /* Fill the send buffer from the resident state.  Needed before the first interval only: afterwards the
  * window kernel has already done it. */
 int hlm_route_pack(hlm_ctx* ctx);
-/* inflow[i] = sum of upstream discharge for the next interval; dev_halo (device pointer) may be NULL
- * when no entry of up_idx is negative.  Queued on the context's stream. */
+/* inflow[i] = sum of upstream discharge for the next interval; dev_halo (device pointer, at least as long as
+ * the largest halo slot up_idx refers to) may be NULL only when no entry of up_idx is negative.  Queued on
+ * the context's stream. */
 int hlm_route_gather(hlm_ctx* ctx, const double* dev_halo);
 /* Download the current inflow [ns] and send buffer [n_send] (either may be NULL).  Synchronises. */
 int hlm_route_peek(hlm_ctx* ctx, double* out_qin, double* out_send);

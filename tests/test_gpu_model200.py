@@ -115,6 +115,30 @@ def test_routed_single_rank_equals_oracle_bit_for_bit(solver):
     assert (qin > 0).sum() > ns // 3          # the inflow really reached the kernel
 
 
+def test_routing_errors_are_loud(solver):
+    from tiger_hlm_gpu_b200 import HlmError
+    sp, col, pr, t2m, y0 = inputs(64)
+    upload(solver, sp, col, pr, t2m)
+    up_ptr = np.arange(65, dtype=np.int64)
+    try:
+        with pytest.raises(HlmError, match="upstream index out of range"):
+            solver.route_set_topology(up_ptr, np.full(64, 64, np.int32))
+        with pytest.raises(HlmError, match="not ascending|bad CSR"):
+            solver.route_set_topology(up_ptr[::-1].copy(), np.zeros(64, np.int32))
+        solver.route_set_topology(up_ptr, np.full(64, -3, np.int32))          # every link fed by halo slot 2
+        solver.solve_begin(200, y0, 0.0, 60.0, [60.0])
+        with pytest.raises(HlmError, match="3 halo elements"):
+            solver.route_gather(None)
+        solver.solve_end()
+        solver.route_set_topology(np.zeros(11, np.int64), np.zeros(0, np.int32))   # a topology for 10 links
+        solver.solve_begin(200, y0, 0.0, 60.0, [60.0])
+        with pytest.raises(HlmError, match="another link count"):
+            solver.solve_window(1)
+        solver.solve_end()
+    finally:
+        solver.route_clear()
+
+
 def test_two_ranks_on_one_gpu_equal_one_rank_bit_for_bit():
     """Two device contexts play two ranks; the all-gather is done by hand through a device buffer.  The
     boundary discharge comes from the window kernel's epilogue (send buffer), not from a pack kernel."""

@@ -143,7 +143,7 @@ struct hlm_ctx {
 
     // routed runs (models with upstream inflow): topology of the links this context owns
     bool routed = false;
-    long long route_ns = 0, route_nnz = 0, route_n_send = 0;
+    long long route_ns = 0, route_nnz = 0, route_n_send = 0, route_halo_need = 0;
     DevBuf<long long> up_ptr;
     DevBuf<int> up_idx, send_idx, send_slot;
     DevBuf<double> qin, own_send;
@@ -1108,8 +1108,11 @@ int hlm_route_set_topology(hlm_ctx* c, const long long* up_ptr, const int* up_id
     const long long ld = (ns + 31) & ~31LL;
     for (long long i = 0; i < ns; ++i)
         if (up_ptr[i + 1] < up_ptr[i]) return fail(HLM_ERR_INVALID, "hlm_route_set_topology: up_ptr is not ascending");
-    for (long long e = 0; e < nnz; ++e)
+    long long halo_need = 0;  // halo elements the topology refers to
+    for (long long e = 0; e < nnz; ++e) {
         if (up_idx[e] >= ns) return fail(HLM_ERR_INVALID, "hlm_route_set_topology: upstream index out of range");
+        if (up_idx[e] < 0) halo_need = std::max<long long>(halo_need, -((long long)up_idx[e] + 1) + 1);
+    }
     std::vector<int> slot;
     try { slot.assign((size_t)ld, -1); } catch (const std::bad_alloc&) { return fail(HLM_ERR_NOMEM, "hlm_route_set_topology: out of host memory"); }
     for (long long k = 0; k < n_send; ++k) {
@@ -1134,6 +1137,7 @@ int hlm_route_set_topology(hlm_ctx* c, const long long* up_ptr, const int* up_id
     c->route_ns = ns;
     c->route_nnz = nnz;
     c->route_n_send = n_send;
+    c->route_halo_need = halo_need;
     c->send_buf = c->own_send.p;
     return HLM_OK;
 }
@@ -1178,6 +1182,9 @@ int hlm_route_gather(hlm_ctx* c, const double* dev_halo) {
     HLM_REQUIRE(c, "hlm_route_gather: ctx is NULL");
     if (!c->routed || !c->in_session) return fail(HLM_ERR_STATE, "hlm_route_gather: needs a topology and a session");
     if (c->route_ns != c->ns) return fail(HLM_ERR_STATE, "hlm_route_gather: topology was set for another link count");
+    if (c->route_halo_need > 0 && !dev_halo)
+        return fail(HLM_ERR_INVALID, "hlm_route_gather: the topology refers to " + std::to_string(c->route_halo_need) +
+                                         " halo elements but no halo vector was given");
     if (int r = use_device(c)) return r;
     const int tpb = 256;
     route_gather_kernel<<<(unsigned)((c->ns + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, dev_halo, c->up_ptr.p,
