@@ -51,10 +51,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="model204", choices=["model204", "routed"],
-                    help="model204 = BASELINE configs[3] (the headline); routed = configs[4]: Model 200 links coupled "
+    ap.add_argument("--workload", default="model204", choices=["model204", "model200", "routed"],
+                    help="model204 = BASELINE configs[3] (the headline); model200 = configs[2]: the project-defined hillslope-"
+                         "link model, unrouted, 1M links, 30 days of forcing; routed = configs[4]: Model 200 links coupled "
                          "through upstream discharge, partitioned by sub-basin, boundary links exchanged over NCCL")
-    ap.add_argument("--links-per-gpu", type=int, default=None, help="default 10M (model204) / 2.5M (routed)")
+    ap.add_argument("--links-per-gpu", type=int, default=None, help="default 10M (model204) / 1M (model200) / 2.5M (routed)")
     ap.add_argument("--couple-minutes", type=float, default=15.0, help="routed: coupling interval")
     ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes"],
                     help="how links are dealt to lanes (hlm_set_schedule); auto = lanes for routed runs, tiles otherwise")
@@ -64,6 +65,8 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--rtol", type=float, default=None, help="override rtol (default 1e-6)")
     ap.add_argument("--atol", type=float, default=None, help="override atol (default 1e-9)")
+    ap.add_argument("--stiff-fallback", action="store_true",
+                    help="continue links the RK45 path flags stiff with the Radau IIA fallback (always on for model200/routed)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / reference_cuda legs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
@@ -368,8 +371,9 @@ def run_routed_arm(args):
 
 
 def workload_config(args, ns):
-    return {"workload": "Model204 hillslope-link runoff, synthetic links (SURVEY 8(d) inputs), 1-year hourly "
-                        "pr + daily t2m forcing grid, hourly dense output; one step = one simulated day "
+    name = ("Model204 hillslope-link runoff, synthetic links (SURVEY 8(d) inputs), 1-year hourly " if args.workload != "model200"
+            else "Model 200 (project-defined hillslope-link runoff, unrouted; BASELINE configs[2]), synthetic links, 30 days of hourly ")
+    return {"workload": name + "pr + daily t2m forcing grid, hourly dense output; one step = one simulated day "
                         "(24 queries) for every link",
             "links_per_gpu": ns, "days_of_forcing": args.days, "queries_per_step": 24,
             "wet_fraction": args.wet_fraction, "rtol": PRM6[1], "atol": PRM6[2], "initial_step": PRM6[0],
@@ -385,7 +389,14 @@ def main():
     if args.atol is not None:
         PRM6[2] = args.atol
     if args.links_per_gpu is None:
-        args.links_per_gpu = 10_000_000 if args.workload == "model204" else 2_500_000
+        args.links_per_gpu = {"model204": 10_000_000, "model200": 1_000_000, "routed": 2_500_000}[args.workload]
+    if args.workload == "model200":
+        if args.days == 365:
+            args.days = 30
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference names model 200 (README.md:95) but ships no "
+                              "definition of it: there is no reference implementation of this workload"}))
+            return
     if args.workload == "routed":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the reference couples no links (SURVEY 8(a) row 9): "
@@ -423,7 +434,10 @@ def main():
     from tiger_hlm_gpu_b200.sharding import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
 
+    uid = 200 if args.workload == "model200" else 204
     sp, col, ncells, pr, t2m, y0 = make_inputs(ns, args.days, args.wet_fraction, rank)
+    if uid == 200:  # channel discharge in place of the snow store
+        y0[:, 0] = np.random.default_rng(7 + rank).uniform(0.05, 5.0, ns)
     solver = hlm.Solver(local_rank)
     # a dedicated non-default stream: the library treats handle 0 as "use my own stream", and torch
     # events only see the stream they are recorded on
@@ -433,7 +447,8 @@ def main():
     solver.set_stream(stream.cuda_stream)
     solver.set_precision(args.precision)
     solver.set_schedule(args.schedule)
-    solver.set_model_parameters(204, hlm.Parameters(*PRM6))
+    solver.set_model_parameters(uid, hlm.Parameters(*PRM6))
+    solver.set_stiff_fallback(args.stiff_fallback or uid == 200)
     solver.set_max_attempts(5_000_000)
     solver.upload_spatial_params(sp)
     solver.upload_forcing(0, 1.0, pr)
@@ -448,7 +463,7 @@ def main():
     def day_queries(k):
         return k * DAY + 60.0 * np.arange(1, 25)
 
-    solver.solve_begin(204, y0, 0.0, DAY, day_queries(0))
+    solver.solve_begin(uid, y0, 0.0, DAY, day_queries(0))
     for k in range(W):
         if k:
             solver.solve_restart(k * DAY, (k + 1) * DAY, day_queries(k))
@@ -502,7 +517,7 @@ def main():
             t0 = k * DAY
             tqw = t0 + 60.0 * np.arange(1, nq_w + 1)
             y_in, y_out = bufs[k % 2], bufs[(k + 1) % 2]
-            rc = lib.hlm_run_rk45(solver._h, 204, C.c_void_p(y_in.data_ptr()), ns, t0, t0 + DAY,
+            rc = lib.hlm_run_rk45(solver._h, uid, C.c_void_p(y_in.data_ptr()), ns, t0, t0 + DAY,
                                   tqw.ctypes.data_as(C.c_void_p), nq_w, C.c_void_p(y_out.data_ptr()),
                                   C.c_void_p(d_host.data_ptr()), C.c_void_p(stiff.data_ptr()),
                                   C.c_void_p(na.data_ptr()), None, None)
@@ -530,12 +545,12 @@ def main():
         d2h = ns * 5 * 8 + ns * nq_w * 5 * 8 + ns * 4 + ns * 4
         e2e = {"value": acc_e_all / (e_ms_max * 1e-3), "unit": "accepted system-steps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms_max / K,
-               "api": "hlm_run_rk45 (C ABI under rk45_api::run_rk45<Model204>), pinned host buffers"}
+               "api": f"hlm_run_rk45 (C ABI under rk45_api::run_rk45<Model{uid}>), pinned host buffers"}
 
     # ---------------- baselines (rank 0, N == 1 only) ----------------
     cpu = None
     ref_cuda = None
-    if rank == 0 and world == 1 and not args.no_baselines:
+    if rank == 0 and world == 1 and not args.no_baselines and uid == 204:
         try:
             cpu = cpu_baseline("port", args, args.cpu_seconds)
         except Exception as ex:  # the oracle library always exists; report rather than hide a failure
@@ -560,7 +575,7 @@ def main():
             ref_cuda = {"error": repr(ex)}
 
     notebook = None
-    if rank == 0 and world == 1 and not args.no_baselines:
+    if rank == 0 and world == 1 and not args.no_baselines and uid == 204:
         # the reference's CPU path as the north star names it: the notebook's SciPy integrator, one process per core
         try:
             from oracle import notebook_baseline as NB
@@ -579,7 +594,8 @@ def main():
         hbm_peak, hbm_src = peaks()
         kern_avg_ms = kern_ms_all / max(kern_n_all, 1)
         att_per_launch = att_all / max(kern_n_all, 1)
-        achieved_tflops = W_MIN_FLOP_PER_ATTEMPT * att_per_launch / (kern_avg_ms * 1e-3) / 1e12
+        w_min = W_MIN_FLOP_PER_ATTEMPT if uid == 204 else W_MIN_FLOP_PER_ATTEMPT_200
+        achieved_tflops = w_min * att_per_launch / (kern_avg_ms * 1e-3) / 1e12
         # algorithmic HBM bytes per link per window: state in+out, prepared parameters, forcing column,
         # dense records, counters
         bytes_per_link = (5 + 2) * 8 * 2 + 6 * 4 * 2 + 11 * 8 + 4 + 24 * 5 * 8
@@ -597,12 +613,12 @@ def main():
                          "frac": achieved_tflops / fp_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
                          # (profiles/r1h_ncu_full_window_kernel_10M.csv: this command, 10 M links, 24 queries), per link
-                         "traffic": (DRAM_BYTES_PER_LINK_PER_LAUNCH * ns if args.precision == 64 and args.wet_fraction == 0.0 else None),
+                         "traffic": (DRAM_BYTES_PER_LINK_PER_LAUNCH * ns if args.precision == 64 and args.wet_fraction == 0.0 and uid == 204 else None),
                          "traffic_source": "ncu --set full capture of this command (profiles/r1h_ncu_full_window_kernel_10M.csv), per link x links",
                          "peak_source": "measured live: register-resident FMA microbenchmark (hlm_measure_fma_peak); "
                                         "MEASURED_PEAKS.json holds no FP64/FP32 vector peak",
-                         "flop_per_attempt": W_MIN_FLOP_PER_ATTEMPT, "attempts_per_launch": att_per_launch,
-                         "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_window_kernel<Model204,double>",
+                         "flop_per_attempt": w_min, "attempts_per_launch": att_per_launch,
+                         "kernel_ms_avg": kern_avg_ms, "kernel": f"hlm::rk45_window_kernel<Model{uid},{'double' if args.precision == 64 else 'float'}>",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_link_per_launch": bytes_per_link}},
             "cpu_baseline": cpu, "notebook_cpu": notebook, "reference_cuda": ref_cuda, "clocks": clocks, "host_binding": numa,

@@ -350,8 +350,11 @@ cudaEvent_t get_event(hlm_ctx* c) {
 
 template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     // schedule: tiles (a warp stays with 32 consecutive links) or lane refill (rk45_window.cuh); by default
-    // lanes for routed runs, whose links take unlike numbers of attempts per launch, tiles otherwise
-    const bool lanes = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && c->routed);
+    // lanes where links take unlike numbers of attempts per launch — Model 200 (the channel's pace grows with
+    // its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
+    // tiles otherwise
+    const bool lanes = c->schedule == HLM_SCHEDULE_LANES ||
+                       (c->schedule == HLM_SCHEDULE_AUTO && (c->routed || Model::HAS_INFLOW));
     static int blocks_per_sm[2] = {0, 0};
     if (blocks_per_sm[lanes] == 0) {
         if (lanes)
