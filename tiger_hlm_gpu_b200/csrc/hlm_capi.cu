@@ -20,6 +20,18 @@
 #include "../../include/hlm_b200.h"
 #include "rk45_window.cuh"
 
+// rk45_instance.cu: the integration kernels, one translation unit per (model, number type)
+namespace hlm {
+#define HLM_DECLARE_LAUNCHER(name) cudaError_t name(bool lanes, const WindowArgs& a, int sm_count, cudaStream_t stream)
+HLM_DECLARE_LAUNCHER(launch_rk45_204_f64);
+HLM_DECLARE_LAUNCHER(launch_rk45_204_f32);
+HLM_DECLARE_LAUNCHER(launch_rk45_200_f64);
+HLM_DECLARE_LAUNCHER(launch_rk45_200_f32);
+HLM_DECLARE_LAUNCHER(launch_rk45_dummy_f64);
+HLM_DECLARE_LAUNCHER(launch_rk45_dummy_f32);
+#undef HLM_DECLARE_LAUNCHER
+}  // namespace hlm
+
 // radau_fallback.cu (its own translation unit: built without FMA contraction)
 namespace hlm {
 cudaError_t radau_launch(int uid, const WindowArgs& a, int* list, unsigned int* n_list, unsigned int* n_radau,
@@ -348,44 +360,28 @@ cudaEvent_t get_event(hlm_ctx* c) {
     return e;
 }
 
-template <class Model, typename T> int launch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
-    // schedule: tiles (a warp stays with 32 consecutive links) or lane refill (rk45_window.cuh); by default
-    // lanes where links take unlike numbers of attempts per launch — Model 200 (the channel's pace grows with
-    // its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
-    // tiles otherwise
-    const bool lanes = c->schedule == HLM_SCHEDULE_LANES ||
-                       (c->schedule == HLM_SCHEDULE_AUTO && (c->routed || Model::HAS_INFLOW));
-    static int blocks_per_sm[2] = {0, 0};
-    if (blocks_per_sm[lanes] == 0) {
-        if (lanes)
-            HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], hlm::rk45_lanes_kernel<Model, T>, 128, 0));
-        else
-            HLM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], hlm::rk45_window_kernel<Model, T>, 128, 0));
-        if (blocks_per_sm[lanes] < 1) blocks_per_sm[lanes] = 1;
-    }
-    long long grid = std::min<long long>((a.n_tiles + 3) / 4, (long long)c->sm_count * blocks_per_sm[lanes]);
-    if (grid < 1) grid = 1;
+// One window launch.  Schedule: tiles (a warp stays with 32 consecutive links) or lane refill (rk45_window.cuh);
+// by default lanes where links take unlike numbers of attempts per launch — Model 200 (the channel's pace grows
+// with its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
+// tiles otherwise.  The kernels live in rk45_instance.cu, one translation unit per (model, number type).
+int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
+    using Launcher = cudaError_t (*)(bool, const hlm::WindowArgs&, int, cudaStream_t);
+    Launcher launch = nullptr;
+    bool divergent_model = false;
+    const bool f32 = c->precision == 32;
+    if (c->uid == hlm::Model204::UID) launch = f32 ? hlm::launch_rk45_204_f32 : hlm::launch_rk45_204_f64;
+    else if (c->uid == hlm::Model200::UID) { launch = f32 ? hlm::launch_rk45_200_f32 : hlm::launch_rk45_200_f64; divergent_model = true; }
+    else if (c->uid == hlm::DummyModel::UID) launch = f32 ? hlm::launch_rk45_dummy_f32 : hlm::launch_rk45_dummy_f64;
+    else return fail(HLM_ERR_INVALID, "unknown model uid");
+    const bool lanes = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && (c->routed || divergent_model));
     HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     HLM_CUDA(cudaEventRecord(e0, c->stream));
-    if (lanes) hlm::rk45_lanes_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
-    else hlm::rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, c->stream>>>(a);
-    HLM_CUDA(cudaGetLastError());
+    HLM_CUDA(launch(lanes, a, c->sm_count, c->stream));
     HLM_CUDA(cudaEventRecord(e1, c->stream));
     c->timing.emplace_back(e0, e1);
     ++c->launches;
     return 0;
-}
-
-int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
-    if (c->uid == hlm::Model204::UID)
-        return c->precision == 32 ? launch_window<hlm::Model204, float>(c, a) : launch_window<hlm::Model204, double>(c, a);
-    if (c->uid == hlm::Model200::UID)
-        return c->precision == 32 ? launch_window<hlm::Model200, float>(c, a) : launch_window<hlm::Model200, double>(c, a);
-    if (c->uid == hlm::DummyModel::UID)
-        return c->precision == 32 ? launch_window<hlm::DummyModel, float>(c, a)
-                                  : launch_window<hlm::DummyModel, double>(c, a);
-    return fail(HLM_ERR_INVALID, "unknown model uid");
 }
 
 // links flagged stiff by the window kernel just queued -> list -> implicit integration of the same window
