@@ -57,6 +57,9 @@ def parse_args():
                          "through upstream discharge, partitioned by sub-basin, boundary links exchanged over NCCL")
     ap.add_argument("--links-per-gpu", type=int, default=None, help="default 10M (model204) / 1M (model200) / 2.5M (routed)")
     ap.add_argument("--couple-minutes", type=float, default=15.0, help="routed: coupling interval")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="routed: boundary discharge all-gathered over NCCL, or stored into every rank's halo vector by the "
+                         "kernels themselves (CUDA IPC peer memory) with a one-element all-reduce as the barrier")
     ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes"],
                     help="how links are dealt to lanes (hlm_set_schedule); auto = lanes for routed runs, tiles otherwise")
     ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
@@ -273,7 +276,7 @@ def run_routed_arm(args):
     solver.set_forcing_columns(col_all[sel])
     del sp_all
     fp_peak = solver.measure_fma_peak(64)
-    rs = routing.RoutedSolver(solver, 200, topo, world, plan.max_send, dist)
+    rs = routing.RoutedSolver(solver, 200, topo, world, plan.max_send, dist, exchange=args.exchange)
     stream = rs.stream
 
     def hour(k, first=False):
@@ -349,7 +352,9 @@ def run_routed_arm(args):
                        "links_per_gpu": args.links_per_gpu, "links_total": ns_all, "couple_minutes": dt,
                        "intervals_per_step": n_int, "schedule": args.schedule, "sub_basins": plan.n_subbasins, "cut_edges": plan.n_cut_edges,
                        "halo_doubles": plan.halo_len, "rtol": PRM6[1], "atol": PRM6[2],
-                       "parallelism": f"sub-basins dealt to {world} GPU(s); one NCCL all-gather of the boundary vector per interval"
+                       "parallelism": (f"sub-basins dealt to {world} GPU(s); " +
+                                       ("boundary discharge stored into peer memory by the kernels, one barrier per interval" if rs.peer
+                                        else "one NCCL all-gather of the boundary vector per interval"))
                                       if world > 1 else "1 GPU, no exchange",
                        "l2": "inputs larger than L2 (state + parameters of the rank's links >> 126 MB)"},
             "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),

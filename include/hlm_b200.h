@@ -243,6 +243,19 @@ int hlm_route_pack(hlm_ctx* ctx);
  * the largest halo slot up_idx refers to) may be NULL only when no entry of up_idx is negative.  Queued on
  * the context's stream. */
 int hlm_route_gather(hlm_ctx* ctx, const double* dev_halo);
+/* Peer-memory exchange, for ranks that are processes on ONE node (NVLink/NVSwitch): instead of a send buffer that
+ * a collective moves, every rank's halo vector is mapped into every other rank's address space (CUDA IPC) and the
+ * integration kernel's epilogue stores each boundary link's discharge straight into all of them — the transfer is
+ * part of the compute kernel, and what remains between intervals is a barrier (any collective on the stream) so
+ * that every rank's stores have landed before hlm_route_gather reads.  Two parities alternate, so a fast rank
+ * never overwrites what a slow one still reads.  Sequence: every rank hlm_route_peer_alloc (gets a 64-byte IPC
+ * handle), the handles are all-gathered by the host ([world][64] bytes, rank order), every rank
+ * hlm_route_peer_open; from then on hlm_route_pack and the kernels publish to the peers and hlm_route_gather
+ * ignores its argument and reads the rank's own halo vector.  hlm_route_peer_close (after a barrier: peers may
+ * still be storing) returns to the send-buffer scheme.  max_send = the plan's segment length. */
+int hlm_route_peer_alloc(hlm_ctx* ctx, int world, int rank, long long max_send, void* ipc_handle_out);
+int hlm_route_peer_open(hlm_ctx* ctx, const void* handles);
+int hlm_route_peer_close(hlm_ctx* ctx);
 /* Download the current inflow [ns] and send buffer [n_send] (either may be NULL).  Synchronises. */
 int hlm_route_peek(hlm_ctx* ctx, double* out_qin, double* out_send);
 

@@ -190,12 +190,15 @@ def test_two_ranks_on_one_gpu_equal_one_rank_bit_for_bit():
     assert np.array_equal(fin, fin_o)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (the NCCL exchange itself); run by tools/routed_check.py under torchrun")
-def test_nccl_exchange_two_gpus():
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (the exchange itself); run by tools/routed_check.py under torchrun")
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
+def test_exchange_two_gpus(mode):
+    """Two processes, two GPUs: boundary discharge all-gathered over NCCL, or stored into the peers' halo vectors by
+    the integration kernels (CUDA IPC) with a one-element all-reduce as the barrier — bit-identical to one rank."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tools", "routed_check.py")],
-                         capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641" if mode == "nccl" else "29642", os.path.join(root, "tools", "routed_check.py")]
+    out = subprocess.run(cmd + (["--peer"] if mode == "peer" else []), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "routed_check ok" in out.stdout
+    assert "routed_check ok" in out.stdout and ("peer memory" in out.stdout) == (mode == "peer")

@@ -75,6 +75,9 @@ SIGNATURES = {
     "hlm_route_pack": (_I, [_V]),
     "hlm_route_gather": (_I, [_V, _V]),
     "hlm_route_peek": (_I, [_V, _V, _V]),
+    "hlm_route_peer_alloc": (_I, [_V, _I, _I, _LL, _V]),
+    "hlm_route_peer_open": (_I, [_V, _V]),
+    "hlm_route_peer_close": (_I, [_V]),
     "hlm_launch_count": (_LL, [_V]),
     "hlm_kernel_time_ms": (_I, [_V, C.POINTER(_D), C.POINTER(_LL)]),
     "hlm_measure_fma_peak": (_I, [_V, _I, C.POINTER(_D)]),
@@ -316,6 +319,20 @@ class Solver:
 
     def route_gather(self, dev_halo: int | None = None):
         _check(self._lib.hlm_route_gather(self._h, _V(dev_halo) if dev_halo else None))
+
+    def route_peer_alloc(self, world: int, rank: int, max_send: int) -> bytes:
+        """Allocate this rank's halo vector for the peer-memory exchange; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        _check(self._lib.hlm_route_peer_alloc(self._h, world, rank, max_send, C.cast(buf, _V)))
+        return bytes(buf.raw)
+
+    def route_peer_open(self, handles: bytes):
+        """Map every rank's halo vector: `handles` = the ranks' 64-byte IPC handles, concatenated in rank order."""
+        buf = C.create_string_buffer(handles, len(handles))
+        _check(self._lib.hlm_route_peer_open(self._h, C.cast(buf, _V)))
+
+    def route_peer_close(self):
+        _check(self._lib.hlm_route_peer_close(self._h))
 
     def route_peek(self):
         ns, n_send = self._route

@@ -160,6 +160,12 @@ struct hlm_ctx {
     DevBuf<int> up_idx, send_idx, send_slot;
     DevBuf<double> qin, own_send;
     double* send_buf = nullptr;  // own_send.p or the caller's (a buffer its collective reads)
+    // peer-memory exchange: every rank's halo vector (two parities) mapped here through CUDA IPC
+    int peer_world = 0, peer_rank = 0;
+    long long peer_max_send = 0, route_epoch = 0;
+    double* own_halo = nullptr;           // cudaMalloc'ed: [2][peer_world * peer_max_send]
+    std::vector<void*> peer_opened;       // cudaIpcOpenMemHandle results (nullptr at peer_rank)
+    DevBuf<double*> peer_ptrs;            // device copy of the world pointers
 
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // per window kernel
@@ -311,10 +317,17 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
 }
 
 // ---- routing: boundary pack and upstream gather (HBM-bound plumbing around the window kernel) ----
+// peer_halo != nullptr: store into every rank's halo vector (peer memory) instead of the send buffer
 __global__ void route_pack_kernel(const double* __restrict__ q, const int* __restrict__ send_idx, long long n_send,
-                                  double* __restrict__ send_buf) {
+                                  double* __restrict__ send_buf, double* const* __restrict__ peer_halo, int peer_world,
+                                  long long peer_off) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n_send) send_buf[k] = q[send_idx[k]];
+    if (k >= n_send) return;
+    const double v = q[send_idx[k]];
+    if (peer_halo != nullptr)
+        for (int r = 0; r < peer_world; ++r) peer_halo[r][peer_off + k] = v;
+    else
+        send_buf[k] = v;
 }
 
 // qin[i] = sum of the discharge of link i's upstream links, added in the order the topology lists them
@@ -450,6 +463,9 @@ void hlm_destroy(hlm_ctx* c) {
         if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
     }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (void* p : c->peer_opened)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (c->own_halo) cudaFree(c->own_halo);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     for (cudaEvent_t ev : c->chunk_ready) cudaEventDestroy(ev);
@@ -757,6 +773,11 @@ static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, double* dens
         a.qin = c->qin.p;
         a.send_slot = c->route_n_send > 0 ? c->send_slot.p : nullptr;
         a.send_buf = c->send_buf;
+        if (c->peer_world > 1) {  // results of this interval are read at parity route_epoch % 2 by the next gather
+            a.peer_halo = c->peer_ptrs.p;
+            a.peer_world = c->peer_world;
+            a.peer_off = (c->route_epoch % 2) * (long long)c->peer_world * c->peer_max_send + (long long)c->peer_rank * c->peer_max_send;
+        }
     }
     if (int r = dispatch_window(c, a)) return r;
     if (c->stiff_fallback)
@@ -1168,10 +1189,16 @@ int hlm_route_pack(hlm_ctx* c) {
     HLM_REQUIRE(c, "hlm_route_pack: ctx is NULL");
     if (!c->routed || !c->in_session) return fail(HLM_ERR_STATE, "hlm_route_pack: needs a topology and a session");
     if (int r = use_device(c)) return r;
-    if (c->route_n_send == 0) return HLM_OK;
+    if (c->route_n_send == 0) {
+        c->route_epoch = 0;
+        return HLM_OK;
+    }
     const int tpb = 256;
-    route_pack_kernel<<<(unsigned)((c->route_n_send + tpb - 1) / tpb), tpb, 0, c->stream>>>(c->y.p, c->send_idx.p,
-                                                                                          c->route_n_send, c->send_buf);
+    c->route_epoch = 0;  // the initial state is what the first gather reads, at parity 0
+    const bool peer = c->peer_world > 1;
+    route_pack_kernel<<<(unsigned)((c->route_n_send + tpb - 1) / tpb), tpb, 0, c->stream>>>(
+        c->y.p, c->send_idx.p, c->route_n_send, c->send_buf, peer ? c->peer_ptrs.p : nullptr, c->peer_world,
+        (long long)c->peer_rank * c->peer_max_send);
     HLM_CUDA(cudaGetLastError());
     ++c->launches;
     return HLM_OK;
@@ -1181,6 +1208,12 @@ int hlm_route_gather(hlm_ctx* c, const double* dev_halo) {
     HLM_REQUIRE(c, "hlm_route_gather: ctx is NULL");
     if (!c->routed || !c->in_session) return fail(HLM_ERR_STATE, "hlm_route_gather: needs a topology and a session");
     if (c->route_ns != c->ns) return fail(HLM_ERR_STATE, "hlm_route_gather: topology was set for another link count");
+    if (c->peer_world > 1) {  // the halo is this rank's own vector, filled by the peers' kernels
+        if (c->route_halo_need > (long long)c->peer_world * c->peer_max_send)
+            return fail(HLM_ERR_INVALID, "hlm_route_gather: the topology refers to halo elements beyond the peer halo vector");
+        dev_halo = c->own_halo + (c->route_epoch % 2) * (long long)c->peer_world * c->peer_max_send;
+        ++c->route_epoch;
+    }
     if (c->route_halo_need > 0 && !dev_halo)
         return fail(HLM_ERR_INVALID, "hlm_route_gather: the topology refers to " + std::to_string(c->route_halo_need) +
                                          " halo elements but no halo vector was given");
@@ -1202,6 +1235,71 @@ int hlm_route_peek(hlm_ctx* c, double* out_qin, double* out_send) {
         HLM_CUDA(cudaMemcpyAsync(out_send, c->send_buf, sizeof(double) * (size_t)c->route_n_send, cudaMemcpyDeviceToHost, c->stream));
     HLM_CUDA(cudaStreamSynchronize(c->stream));
     return HLM_OK;
+}
+
+// ---- peer-memory exchange for routed runs ----------------------------------------------------------
+
+static int peer_close_impl(hlm_ctx* c) {
+    for (void* p : c->peer_opened)
+        if (p) cudaIpcCloseMemHandle(p);
+    c->peer_opened.clear();
+    if (c->own_halo) cudaFree(c->own_halo);
+    c->own_halo = nullptr;
+    c->peer_world = 0;
+    c->peer_rank = 0;
+    c->peer_max_send = 0;
+    return HLM_OK;
+}
+
+int hlm_route_peer_alloc(hlm_ctx* c, int world, int rank, long long max_send, void* ipc_handle_out) {
+    HLM_REQUIRE(c && ipc_handle_out && world > 1 && rank >= 0 && rank < world && max_send > 0, "hlm_route_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI documents a 64-byte handle");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    peer_close_impl(c);
+    const size_t n = 2 * (size_t)world * (size_t)max_send;
+    HLM_CUDA(cudaMalloc(&c->own_halo, n * sizeof(double)));
+    HLM_CUDA(cudaMemset(c->own_halo, 0, n * sizeof(double)));
+    cudaIpcMemHandle_t h;
+    HLM_CUDA(cudaIpcGetMemHandle(&h, c->own_halo));
+    std::memcpy(ipc_handle_out, &h, sizeof(h));
+    c->peer_world = -world;  // allocated, peers not mapped yet (kernels keep using the send buffer)
+    c->peer_rank = rank;
+    c->peer_max_send = max_send;
+    return HLM_OK;
+}
+
+int hlm_route_peer_open(hlm_ctx* c, const void* handles) {
+    HLM_REQUIRE(c && handles, "hlm_route_peer_open: NULL argument");
+    if (c->peer_world >= 0 || !c->own_halo) return fail(HLM_ERR_STATE, "hlm_route_peer_open: call hlm_route_peer_alloc first");
+    if (int r = use_device(c)) return r;
+    const int world = -c->peer_world;
+    std::vector<double*> ptrs((size_t)world, nullptr);
+    c->peer_opened.assign((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == c->peer_rank) {
+            ptrs[(size_t)r] = c->own_halo;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        HLM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened[(size_t)r] = p;
+        ptrs[(size_t)r] = static_cast<double*>(p);
+    }
+    HLM_CUDA(c->peer_ptrs.reserve((size_t)world));
+    HLM_CUDA(cudaMemcpy(c->peer_ptrs.p, ptrs.data(), sizeof(double*) * (size_t)world, cudaMemcpyHostToDevice));
+    c->peer_world = world;
+    c->route_epoch = 0;
+    return HLM_OK;
+}
+
+int hlm_route_peer_close(hlm_ctx* c) {
+    HLM_REQUIRE(c, "hlm_route_peer_close: ctx is NULL");
+    if (int r = use_device(c)) return r;
+    HLM_CUDA(cudaStreamSynchronize(c->stream));
+    return peer_close_impl(c);
 }
 
 int hlm_debug_eval(hlm_ctx* c, int op, const double* x, const double* y, double* out, long long n) {

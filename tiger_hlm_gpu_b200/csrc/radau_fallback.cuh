@@ -259,10 +259,7 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
         a.n_reject[sys] = n_rej;
         ra.n_radau[sys] = n_imp;
         if constexpr (Model::HAS_INFLOW) {
-            if (a.send_slot != nullptr && status != kStiffPaused) {
-                const int slot = __ldg(a.send_slot + sys);
-                if (slot >= 0) a.send_buf[slot] = y[0];
-            }
+            if (status != kStiffPaused) route_publish(a, sys, y[0]);
         }
     }
 }

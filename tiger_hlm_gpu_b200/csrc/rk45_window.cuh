@@ -161,7 +161,26 @@ struct WindowArgs {
     const double* qin;     // [ld]
     const int* send_slot;  // [ld] or nullptr
     double* send_buf;
+    // peer-memory exchange (one process per GPU on one node): instead of a send buffer a collective then moves,
+    // the discharge is stored straight into every rank's halo vector through its IPC-mapped address, element
+    // peer_off + slot (peer_off = parity * halo length + my rank * segment length); nullptr = not in use
+    double* const* peer_halo;  // [peer_world] device pointers (own halo included)
+    int peer_world;
+    long long peer_off;
 };
+
+// Hand a boundary link's discharge to whoever needs it for the next interval (epilogue of the integration
+// kernels and of the fallback): no pack kernel, and with peer memory no collective moving data either.
+__device__ __forceinline__ void route_publish(const WindowArgs& a, long long sys, double q) {
+    if (a.send_slot == nullptr) return;
+    const int slot = __ldg(a.send_slot + sys);
+    if (slot < 0) return;
+    if (a.peer_halo != nullptr) {
+        for (int r = 0; r < a.peer_world; ++r) a.peer_halo[r][a.peer_off + slot] = q;  // NVLink stores (own copy too)
+    } else {
+        a.send_buf[slot] = q;
+    }
+}
 
 template <typename T, int N>
 struct StepOut {
@@ -305,10 +324,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(con
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
-            if (a.send_slot != nullptr && status != kActive) {
-                const int slot = __ldg(a.send_slot + sys);
-                if (slot >= 0) a.send_buf[slot] = (double)y[0];
-            }
+            if (status != kActive) route_publish(a, sys, (double)y[0]);
         }
     }
 }
@@ -403,10 +419,7 @@ template <class Model, typename T> struct LinkRun {
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
-            if (a.send_slot != nullptr && status != kActive) {
-                const int slot = __ldg(a.send_slot + sys);
-                if (slot >= 0) a.send_buf[slot] = (double)y[0];
-            }
+            if (status != kActive) route_publish(a, sys, (double)y[0]);
         }
     }
 };

@@ -205,10 +205,14 @@ class RoutedSolver:
     solver: a tiger_hlm_gpu_b200.Solver with parameters/forcings uploaded for this rank's links (planned
     order).  dist: torch.distributed (NCCL) or None for a single rank.  Everything — window kernel (which
     packs the boundary discharge in its epilogue), all-gather, inflow gather — is queued on torch's current
-    stream; nothing synchronises with the host between intervals.  The implicit fallback is switched on for
+    stream; nothing synchronises with the host between intervals.  exchange = "nccl": the boundary vector is
+    all-gathered; "peer": the kernels store boundary discharge straight into every rank's halo vector over NVLink
+    (CUDA IPC, ranks on one node) and the only collective left is a one-element all-reduce acting as the barrier
+    between intervals.  The implicit fallback is switched on for
     the run: a link the explicit path abandons would otherwise freeze and starve everything downstream."""
 
-    def __init__(self, solver, uid: int, topo: RankTopology, world: int, max_send: int, dist=None, device=None):
+    def __init__(self, solver, uid: int, topo: RankTopology, world: int, max_send: int, dist=None, device=None,
+                 exchange: str = "nccl"):
         import torch
         self.torch = torch
         self.s, self.uid, self.topo, self.world, self.max_send, self.dist = solver, uid, topo, world, max_send, dist
@@ -219,8 +223,18 @@ class RoutedSolver:
         solver.set_stream(self.stream.cuda_stream)
         solver.route_set_topology(topo.up_ptr, topo.up_idx, topo.send_idx)
         solver.set_stiff_fallback(True)
-        self.send = self.halo = None
-        if world > 1 and max_send > 0:
+        self.send = self.halo = self.flag = None
+        self.peer = exchange == "peer" and world > 1 and max_send > 0
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        if self.peer:
+            mine = solver.route_peer_alloc(world, topo.rank, max_send)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            solver.route_peer_open(b"".join(handles))
+            with torch.cuda.stream(self.stream):
+                self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        elif world > 1 and max_send > 0:
             with torch.cuda.stream(self.stream):
                 self.send = torch.zeros(max_send, dtype=torch.float64, device=self.device)
                 self.halo = torch.zeros(world * max_send, dtype=torch.float64, device=self.device)
@@ -229,7 +243,14 @@ class RoutedSolver:
         self.exchanges = 0
 
     def _exchange_and_gather(self):
-        if self.halo is not None:
+        if self.peer:
+            # the data is already in every halo vector (stored by the kernels); all that is needed is that every
+            # rank's kernel has finished before anyone reads: a stream-ordered barrier
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(self.flag)
+            self.exchanges += 1
+            self.s.route_gather(None)
+        elif self.halo is not None:
             with self.torch.cuda.stream(self.stream):
                 self.dist.all_gather_into_tensor(self.halo, self.send)
             self.exchanges += 1
@@ -255,6 +276,9 @@ class RoutedSolver:
 
     def end(self):
         r = self.s.solve_end()
+        if self.peer:
+            self.dist.barrier()          # peers may still be storing into this rank's halo vector
+            self.s.route_peer_close()
         self.s.set_stream(None)
         self.s.set_stiff_fallback(False)
         return r

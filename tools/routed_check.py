@@ -28,7 +28,8 @@ def main():
     sel = p.order[topo.lo:topo.hi]
     s = Solver(local)
     upload(s, sp[sel], col[sel], pr, t2m)
-    rs = routing.RoutedSolver(s, 200, topo, world, p.max_send, dist if world > 1 else None)
+    exchange = "peer" if "--peer" in sys.argv else "nccl"
+    rs = routing.RoutedSolver(s, 200, topo, world, p.max_send, dist if world > 1 else None, exchange=exchange)
     edges = np.arange(0.0, tf + 1e-9, dt)
     for i, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
         tq = np.array([b])
@@ -56,7 +57,8 @@ def main():
         assert np.array_equal(na_g, na_o), "accepted-step counts differ"
         assert np.array_equal(fin.cpu().numpy(), fin_o), "final states differ"
         print(f"routed_check ok: world {world}, {ns} links, {p.n_subbasins} sub-basins, {p.n_cut_edges} cut edges, "
-              f"{rs.exchanges} all-gathers of {p.halo_len} doubles, bit-identical to the single-rank CPU oracle")
+              f"{rs.exchanges} x " + ("barrier (boundary discharge stored into peer memory by the kernels)" if rs.peer else
+                                      f"all-gather of {p.halo_len} doubles") + ", bit-identical to the single-rank CPU oracle")
     if world > 1:
         dist.destroy_process_group()
 
