@@ -175,8 +175,8 @@ inline RoutePlan plan_routes(const std::vector<long long>& stream, const std::ve
 }
 
 /// Per-interval driver of one rank's routed run.  `exchange(d_send, n_send_padded, d_halo)` is the caller's
-/// collective on device buffers (ncclAllGather on the context's stream, or MPI for a CUDA-aware build); it is
-/// not called when world == 1 or nothing crosses ranks.  The implicit fallback is switched on for the run: a
+/// collective on device buffers (ncclAllGather on the context's stream, or MPI for a CUDA-aware build) — or, in
+/// peer mode (hlm_route_peer_*), just a barrier; it is not called when world == 1 or nothing crosses ranks.  The implicit fallback is switched on for the run: a
 /// link the explicit path abandons would freeze and starve everything downstream.
 class RoutedRun {
   public:
@@ -190,8 +190,11 @@ class RoutedRun {
               "hlm_route_set_topology");
         check(hlm_set_stiff_fallback(ctx.get(), 1), "hlm_set_stiff_fallback");
         if (world_ > 1 && max_send_ > 0) {
-            if (!exchange_ || !d_send_ || !d_halo_) throw std::runtime_error("RoutedRun: a multi-rank run needs an exchange and its device buffers");
-            check(hlm_route_set_send_buffer(ctx.get(), d_send_), "hlm_route_set_send_buffer");
+            // with the peer-memory exchange (hlm_route_peer_alloc/open done by the caller) the kernels deliver the
+            // data themselves: the callback is then only a barrier on the stream and the two buffers stay null
+            if (!exchange_) throw std::runtime_error("RoutedRun: a multi-rank run needs an exchange (a collective, or a barrier in peer mode)");
+            if ((d_send_ == nullptr) != (d_halo_ == nullptr)) throw std::runtime_error("RoutedRun: give both device buffers or neither");
+            if (d_send_) check(hlm_route_set_send_buffer(ctx.get(), d_send_), "hlm_route_set_send_buffer");
         }
     }
     ~RoutedRun() {
