@@ -22,7 +22,7 @@
 
 // rk45_instance.cu: the integration kernels, one translation unit per (model, number type)
 namespace hlm {
-#define HLM_DECLARE_LAUNCHER(name) cudaError_t name(bool lanes, const WindowArgs& a, int sm_count, cudaStream_t stream)
+#define HLM_DECLARE_LAUNCHER(name) cudaError_t name(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream)
 HLM_DECLARE_LAUNCHER(launch_rk45_204_f64);
 HLM_DECLARE_LAUNCHER(launch_rk45_204_f32);
 HLM_DECLARE_LAUNCHER(launch_rk45_200_f64);
@@ -378,7 +378,7 @@ cudaEvent_t get_event(hlm_ctx* c) {
 // with its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
 // tiles otherwise.  The kernels live in rk45_instance.cu, one translation unit per (model, number type).
 int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
-    using Launcher = cudaError_t (*)(bool, const hlm::WindowArgs&, int, cudaStream_t);
+    using Launcher = cudaError_t (*)(int, const hlm::WindowArgs&, int, cudaStream_t);
     Launcher launch = nullptr;
     bool divergent_model = false;
     const bool f32 = c->precision == 32;
@@ -390,7 +390,9 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     HLM_CUDA(cudaEventRecord(e0, c->stream));
-    HLM_CUDA(launch(lanes, a, c->sm_count, c->stream));
+    // routed runs take a few attempts per link per launch: the lane kernel that tests for "finished" right
+    // after the attempt (rk45_window.cuh, kEarlyLeave)
+    HLM_CUDA(launch(lanes ? (c->routed ? 2 : 1) : 0, a, c->sm_count, c->stream));
     HLM_CUDA(cudaEventRecord(e1, c->stream));
     c->timing.emplace_back(e0, e1);
     ++c->launches;

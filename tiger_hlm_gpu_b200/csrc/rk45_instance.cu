@@ -11,21 +11,26 @@
 
 namespace hlm {
 
-// lanes: the lane-refill schedule (rk45_lanes_kernel) instead of tiles (rk45_window_kernel).  The grid is
-// SMs x resident CTAs of the kernel (persistent warps pull work from a counter), fewer when there is less work.
-cudaError_t HLM_INST_NAME(bool lanes, const WindowArgs& a, int sm_count, cudaStream_t stream) {
+// schedule 0: tiles (rk45_window_kernel); 1: lane refill; 2: lane refill with the early-leave test (few attempts
+// per link per launch).  The grid is SMs x resident CTAs of the kernel (persistent warps pull work from a
+// counter), fewer when there is less work.
+cudaError_t HLM_INST_NAME(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream) {
     using Model = HLM_INST_MODEL;
     using T = HLM_INST_T;
-    static int blocks_per_sm[2] = {0, 0};
-    if (blocks_per_sm[lanes] == 0) {
-        const cudaError_t e = lanes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], rk45_lanes_kernel<Model, T>, 128, 0)
-                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], rk45_window_kernel<Model, T>, 128, 0);
+    static int blocks_per_sm[3] = {0, 0, 0};
+    if (schedule < 0 || schedule > 2) return cudaErrorInvalidValue;
+    if (blocks_per_sm[schedule] == 0) {
+        cudaError_t e;
+        if (schedule == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], rk45_window_kernel<Model, T>, 128, 0);
+        else if (schedule == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], rk45_lanes_kernel<Model, T, false>, 128, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[2], rk45_lanes_kernel<Model, T, true>, 128, 0);
         if (e != cudaSuccess) return e;
-        if (blocks_per_sm[lanes] < 1) blocks_per_sm[lanes] = 1;
+        if (blocks_per_sm[schedule] < 1) blocks_per_sm[schedule] = 1;
     }
-    const long long grid = std::max<long long>(1, std::min<long long>((a.n_tiles + 3) / 4, (long long)sm_count * blocks_per_sm[lanes]));
-    if (lanes) rk45_lanes_kernel<Model, T><<<(unsigned)grid, 128, 0, stream>>>(a);
-    else rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, stream>>>(a);
+    const long long grid = std::max<long long>(1, std::min<long long>((a.n_tiles + 3) / 4, (long long)sm_count * blocks_per_sm[schedule]));
+    if (schedule == 0) rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, stream>>>(a);
+    else if (schedule == 1) rk45_lanes_kernel<Model, T, false><<<(unsigned)grid, 128, 0, stream>>>(a);
+    else rk45_lanes_kernel<Model, T, true><<<(unsigned)grid, 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

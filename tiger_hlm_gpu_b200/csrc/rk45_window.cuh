@@ -403,6 +403,17 @@ template <class Model, typename T> struct LinkRun {
         return false;
     }
 
+    // The loop's own exit tests (top of the body) would only fire on the NEXT pass, during which the lane would
+    // idle while the others of its warp integrate — with 3 attempts per link that is a quarter of its time.
+    // Same tests, same outcome, one pass earlier.
+    __device__ __forceinline__ bool finished(const WindowArgs& a, const RunConsts<T>& c) {
+        if (!(t < c.tf)) {
+            status = kDone;
+            return true;
+        }
+        return !c.run_to_end && next_q >= a.q_hi;
+    }
+
     // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
     // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
     __device__ __forceinline__ void store(const WindowArgs& a) const {
@@ -431,7 +442,11 @@ template <class Model, typename T> struct LinkRun {
 // and 20 at the tail — where the tile schedule leaves three quarters of the lanes idle.  Loads and stores of a
 // lane are then its own (not coalesced): per link that is ~300 bytes against thousands of FP64 instructions.
 // Per-link arithmetic is the same function, so results are bit-identical under either schedule.
-template <class Model, typename T>
+// kEarlyLeave: test for "link finished" right after the attempt instead of at the top of the next pass (see
+// LinkRun::finished).  Worth it when links take few attempts per launch (routed runs: +10 %); with tens of
+// attempts per link the larger register footprint of the merged control flow costs more than the idle pass
+// (unrouted Model 200: -10 %), so the launcher picks.
+template <class Model, typename T, bool kEarlyLeave>
 __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_lanes_kernel(const WindowArgs a) {
     const unsigned int lane = threadIdx.x & 31;
     const long long first = a.tile_lo << 5;
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_lanes_kernel(cons
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
         }
-        if (have && r.attempt(a, c)) {
+        if (have && (r.attempt(a, c) || (kEarlyLeave && r.finished(a, c)))) {
             r.store(a);
             have = false;
         }
