@@ -154,6 +154,22 @@ def test_plan_invariants():
             assert p.max_send == 0 and p.n_cut_edges == 0
 
 
+def test_plan_leaves_no_rank_empty_and_rejects_too_few_subbasins():
+    import pytest
+    # three sub-basins of very unlike size over three ranks: a share-based cut alone would leave rank 2 empty
+    down = np.concatenate([[-1], np.arange(9), [-1], np.arange(10, 19), [-1], np.arange(20, 99)])
+    stream = 1000 + np.arange(100)
+    nxt = np.where(down >= 0, stream[np.maximum(down, 0)], 0)
+    p = routing.plan(stream, nxt, 3, subbasin_links=1000)
+    assert p.n_subbasins == 3 and [hi - lo for lo, hi in p.ranges] == [10, 10, 80]
+    with pytest.raises(ValueError, match="cannot be dealt"):
+        routing.plan(stream, nxt, 4, subbasin_links=1000)
+    # a network without a single edge: every link is its own sub-basin, nothing to exchange
+    p = routing.plan(stream, np.zeros(100, np.int64), 2)
+    assert p.n_cut_edges == 0 and p.max_send == 0 and all(t.up_idx.size == 0 for t in p.ranks)
+    assert [hi - lo for lo, hi in p.ranges] == [50, 50]
+
+
 def test_three_ranks_with_a_simulated_exchange_equal_one_rank_bit_for_bit():
     sp, down, rain, temp, pr, t2m, y0 = network_case(ns=60, seed=5)
     F = O.Forcing([pr, t2m], [1.0, 24.0])

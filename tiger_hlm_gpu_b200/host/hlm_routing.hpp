@@ -17,6 +17,7 @@
 #include <functional>
 #include <numeric>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "../../include/hlm_b200/rk45_api.hpp"
@@ -99,14 +100,24 @@ inline RoutePlan plan_routes(const std::vector<long long>& stream, const std::ve
         }
         ++count[(size_t)r];
     }
+    if ((long long)roots.size() < world)
+        throw std::runtime_error(std::to_string(roots.size()) + " sub-basins cannot be dealt to " + std::to_string(world) + " ranks: lower subbasin_links");
+    // contiguous runs: a rank is closed when taking half of the next sub-basin would carry it past its share of
+    // the links, or when the sub-basins left are only just enough to give every remaining rank one
     std::vector<long long> rank_of_root((size_t)n, 0);
-    long long cum = 0, prev_rank = 0;
-    for (long long r : roots) {
-        cum += count[(size_t)r];
-        long long rk = std::min<long long>((cum - count[(size_t)r] / 2) * world / std::max<long long>(n, 1), world - 1);
-        rk = std::max(rk, prev_rank);
-        prev_rank = rk;
-        rank_of_root[(size_t)r] = rk;
+    {
+        long long rank = 0, cum = 0, have = 0;
+        for (size_t i = 0; i < roots.size(); ++i) {
+            const long long cnt = count[(size_t)roots[i]];
+            if (rank < world - 1 && have > 0 &&
+                ((2 * cum + cnt) * world > 2 * (rank + 1) * n || (long long)(roots.size() - i) <= world - 1 - rank)) {
+                ++rank;
+                have = 0;
+            }
+            rank_of_root[(size_t)roots[i]] = rank;
+            cum += cnt;
+            have += cnt;
+        }
     }
     std::vector<long long> owner((size_t)n);
     for (long long i = 0; i < n; ++i) owner[(size_t)i] = rank_of_root[(size_t)root[(size_t)i]];

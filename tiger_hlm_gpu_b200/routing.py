@@ -133,9 +133,19 @@ def plan(stream, next_stream, world: int, subbasin_links: int = 4096) -> RoutePl
     roots, first, counts = np.unique(root, return_index=True, return_counts=True)
     by_first = np.argsort(first, kind="stable")
     roots, counts = roots[by_first], counts[by_first]
-    cum = np.cumsum(counts)
-    sb_rank = np.minimum((cum - counts // 2) * world // max(n, 1), world - 1).astype(np.int64)
-    sb_rank = np.maximum.accumulate(sb_rank)
+    if roots.size < world:
+        raise ValueError(f"{roots.size} sub-basins cannot be dealt to {world} ranks: lower subbasin_links")
+    # contiguous runs: a rank is closed when taking half of the next sub-basin would carry it past its share of
+    # the links, or when the sub-basins left are only just enough to give every remaining rank one
+    sb_rank = np.zeros(roots.size, dtype=np.int64)
+    rank, cum, have = 0, 0, 0
+    for i, cnt in enumerate(counts.tolist()):
+        if rank < world - 1 and have > 0 and ((2 * cum + cnt) * world > 2 * (rank + 1) * n or roots.size - i <= world - 1 - rank):
+            rank += 1
+            have = 0
+        sb_rank[i] = rank
+        cum += cnt
+        have += cnt
     rank_of_root = np.empty(n, dtype=np.int64)
     rank_of_root[roots] = sb_rank
     owner = rank_of_root[root]                       # per original link
