@@ -528,7 +528,9 @@ def main():
                                   C.c_void_p(na.data_ptr()), None, None)
             if rc != 0:
                 raise hlm.HlmError(lib.hlm_last_error().decode())
-            return int(na.sum().item())
+            # the step count for the throughput figure comes from the device-side totals (56 bytes), not from a
+            # host pass over the 10 M counters the operator has just returned in `na`
+            return solver.solve_totals()["n_accept"]
 
         for k in range(W):
             one_step(k)
