@@ -143,8 +143,9 @@ int hlm_set_precision(hlm_ctx* ctx, int bits);
 /* ---- the operator ---------------------------------------------------------------------------- */
 
 /* Replaces rk45_api::run_rk45<T>(h_y0, t0, tf, h_query_times, d_sp) (solver/rk45_api.hpp:273-313)
- * = setup_gpu_buffers + launch_rk45_kernel + retrieve_and_free (solver/rk45_api.hpp:63-270), minus
- * the Radau re-integration of flagged links (out of scope).
+ * = setup_gpu_buffers + launch_rk45_kernel + retrieve_and_free (solver/rk45_api.hpp:63-270), the
+ * Radau re-integration of flagged links included when hlm_set_stiff_fallback is on.  A large output
+ * leaves in chunks of links whose copies overlap the integration of the next chunk.
  *   y0          host [ns][N_EQ]
  *   tq          host [nq] ascending query times (may be NULL when nq == 0)
  *   out_final   host [ns][N_EQ]; rows of links that did not reach tf are zero (the reference
