@@ -70,3 +70,42 @@ def test_cpp_routed_example_matches_the_routed_oracle(tmp_path):
     np.testing.assert_allclose(final, fin_o, rtol=6e-6)                                    # 6 significant digits in final.csv
     np.testing.assert_allclose(dense[:, 1:].reshape(n_int, ns, 5).transpose(1, 0, 2), dense_o, rtol=2e-9, atol=5e-10)
     assert fin_o[:, 0].max() > 5 * fin_o[:, 0].min()                                        # discharge accumulates downstream
+
+
+def test_cpp_routed_nccl_two_processes(tmp_path):
+    """hlm_routed_nccl: the C++ host of INTEGRATION.md section 6 — one process per GPU, hlm_b200::plan_routes,
+    RoutedRun with ncclAllGather as the exchange — against the single-rank CPU routed run, bit for bit
+    (final_rank_*.csv carry 17 significant digits)."""
+    import torch
+    from tests import routed_ref
+    from tiger_hlm_gpu_b200 import routing
+    from tiger_hlm_gpu_b200.hostio import load_spatial_params, write_spatial_params_csv
+    exe = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host", "build", "hlm_routed_nccl")
+    if torch.cuda.device_count() < 2 or not os.path.exists(exe):
+        pytest.skip("needs 2 GPUs and the NCCL example")
+    ns, hours, dt, sub, world = 4000, 2.0, 15.0, 128, 2
+    sp = synthetic.apply_network(synthetic.make_spatial_params(ns), synthetic.make_network(ns, subbasin_links=sub, seed=8))
+    csv = str(tmp_path / "params.csv")
+    write_spatial_params_csv(csv, sp)
+    sp = load_spatial_params(csv)
+    procs = [subprocess.Popen([exe, csv, str(tmp_path), str(hours), str(dt), str(sub), "2e-5", "8.0"],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all(" 0 links lost" in o[0] for o in outs) and "all-gathers" in outs[0][0]
+    got = {}
+    for r in range(world):
+        rows = np.loadtxt(tmp_path / f"final_rank_{r}.csv", delimiter=",", skiprows=1)
+        for row in rows:
+            got[int(row[0])] = row[1:]
+    assert len(got) == ns
+    pr = np.full((int(hours + 1.5), ns), 2e-5, np.float32)
+    t2m = np.full((1, ns), 8.0, np.float32)
+    y0 = np.tile(synthetic.Y0_200, (ns, 1))
+    p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=sub)
+    fin_o, _, _, _ = routed_ref.run_single(sp, O.Forcing([pr, t2m], [1.0, 24.0]), y0, O.Params.make(initialStep=1e-6), p1, 0.0,
+                                          hours * 60.0, dt, threads=8)
+    fin_g = np.array([got[int(s)] for s in sp["stream"]])
+    assert np.array_equal(fin_g, fin_o)
+    assert routing.plan(sp["stream"], sp["next_stream"], world, subbasin_links=sub).n_cut_edges > 0
