@@ -21,16 +21,17 @@ cudaError_t HLM_INST_NAME(int schedule, const WindowArgs& a, int sm_count, cudaS
     if (schedule < 0 || schedule > 2) return cudaErrorInvalidValue;
     if (blocks_per_sm[schedule] == 0) {
         cudaError_t e;
-        if (schedule == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], rk45_window_kernel<Model, T>, 128, 0);
-        else if (schedule == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], rk45_lanes_kernel<Model, T, false>, 128, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[2], rk45_lanes_kernel<Model, T, true>, 128, 0);
+        if (schedule == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], rk45_window_kernel<Model, T>, HLM_CTA_THREADS, 0);
+        else if (schedule == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], rk45_lanes_kernel<Model, T, false>, HLM_CTA_THREADS, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[2], rk45_lanes_kernel<Model, T, true>, HLM_CTA_THREADS, 0);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm[schedule] < 1) blocks_per_sm[schedule] = 1;
     }
-    const long long grid = std::max<long long>(1, std::min<long long>((a.n_tiles + 3) / 4, (long long)sm_count * blocks_per_sm[schedule]));
-    if (schedule == 0) rk45_window_kernel<Model, T><<<(unsigned)grid, 128, 0, stream>>>(a);
-    else if (schedule == 1) rk45_lanes_kernel<Model, T, false><<<(unsigned)grid, 128, 0, stream>>>(a);
-    else rk45_lanes_kernel<Model, T, true><<<(unsigned)grid, 128, 0, stream>>>(a);
+    constexpr int kWarps = HLM_CTA_THREADS / 32;
+    const long long grid = std::max<long long>(1, std::min<long long>((a.n_tiles + kWarps - 1) / kWarps, (long long)sm_count * blocks_per_sm[schedule]));
+    if (schedule == 0) rk45_window_kernel<Model, T><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
+    else if (schedule == 1) rk45_lanes_kernel<Model, T, false><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
+    else rk45_lanes_kernel<Model, T, true><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,9 @@
 #ifndef HLM_BLOCKS_PER_SM
 #define HLM_BLOCKS_PER_SM 3
 #endif
+#ifndef HLM_CTA_THREADS
+#define HLM_CTA_THREADS 128  // the kernels only use the lane id: any multiple of 32 works
+#endif
 namespace hlm {
 
 // Dormand–Prince tableau, same expressions as solver/rk45_step_dense.cuh:54-83 so the constants
@@ -257,7 +260,7 @@ __device__ __forceinline__ long long forcing_index(double t, double dt_min, long
 // when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
 // threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
 template <class Model, typename T>
-__global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
+__global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const int lane = threadIdx.x & 31;
@@ -447,7 +450,7 @@ template <class Model, typename T> struct LinkRun {
 // attempts per link the larger register footprint of the merged control flow costs more than the idle pass
 // (unrouted Model 200: -10 %), so the launcher picks.
 template <class Model, typename T, bool kEarlyLeave>
-__global__ void __launch_bounds__(128, HLM_BLOCKS_PER_SM) rk45_lanes_kernel(const WindowArgs a) {
+__global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_lanes_kernel(const WindowArgs a) {
     const unsigned int lane = threadIdx.x & 31;
     const long long first = a.tile_lo << 5;
     const long long last = ((a.tile_lo + a.n_tiles) << 5) < a.ns ? ((a.tile_lo + a.n_tiles) << 5) : a.ns;
