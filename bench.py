@@ -375,6 +375,10 @@ def run_routed_arm(args):
         dist.destroy_process_group()
 
 
+def w_min_for(uid):
+    return W_MIN_FLOP_PER_ATTEMPT if uid == 204 else W_MIN_FLOP_PER_ATTEMPT_200
+
+
 def workload_config(args, ns):
     name = ("Model204 hillslope-link runoff, synthetic links (SURVEY 8(d) inputs), 1-year hourly " if args.workload != "model200"
             else "Model 200 (project-defined hillslope-link runoff, unrouted; BASELINE configs[2]), synthetic links, 30 days of hourly ")
@@ -504,6 +508,41 @@ def main():
         ms, [acc, attempts, launches, kern_ms, kern_n], dist, dev)
     value = acc_all / (ms_max * 1e-3)
 
+    # ---------------- FP32 arm (BASELINE configs[3]: "FP32 vs FP64"): same days, same links, state and stages in FP32 ----
+    fp32 = None
+    if args.precision == 64 and not args.no_baselines:
+        solver.set_precision(32)
+        peak32 = solver.measure_fma_peak(32)
+        solver.solve_begin(uid, y0, 0.0, DAY, day_queries(0))
+        for k in range(W):
+            if k:
+                solver.solve_restart(k * DAY, (k + 1) * DAY, day_queries(k))
+            solver.solve_window(24, True)
+        solver.synchronize()
+        t32a = solver.solve_totals()
+        solver.kernel_time_ms()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        f0.record(stream)
+        for k in range(W, W + K):
+            solver.solve_restart(k * DAY, (k + 1) * DAY, day_queries(k))
+            solver.solve_window(24, True)
+        f1.record(stream)
+        barrier()
+        ms32 = f0.elapsed_time(f1)
+        t32b = solver.solve_totals()
+        solver.solve_end()
+        solver.set_precision(64)
+        acc32 = t32b["n_accept"] - t32a["n_accept"]
+        att32 = acc32 + (t32b["n_reject"] - t32a["n_reject"]) + (t32b["n_jump"] - t32a["n_jump"])
+        ms32_max, (acc32_all, att32_all) = reduce_timing(ms32, [acc32, att32], dist, dev)
+        fp32 = {"value": acc32_all / (ms32_max * 1e-3), "unit": "accepted system-steps/s", "ms_per_step": ms32_max / K,
+                "attempts_per_accepted": att32_all / max(acc32_all, 1.0),
+                "roofline_frac": w_min_for(uid) * att32_all / world / (ms32_max * 1e-3) / 1e12 / peak32, "peak_tflops": peak32,
+                "link_status_after_run": {k: t32b[k] for k in ("active", "done", "stiff", "stalled")},
+                "note": "hlm_set_precision(32): FP32 state, stages and error control; no reference counterpart (the reference is "
+                        "FP64 only), compared with FP64 at rtol 1e-4 in tests/test_gpu_parity.py"}
+
     # ---------------- end-to-end arm: `e2e` ----------------
     e2e = None
     if not args.no_e2e:
@@ -614,7 +653,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, ns),
             "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),
             "link_status_after_run": {k: state[k] for k in ("active", "done", "stiff", "stalled")},
-            "e2e": e2e, "gpu_launches": int(launches_all),
+            "e2e": e2e, "fp32": fp32, "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp64" if args.precision == 64 else "fp32",
                          "achieved": achieved_tflops, "peak": fp_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp_peak,
