@@ -122,7 +122,7 @@ struct Model204 {
         // 4) gravitational (interflow), 5) aquifer (baseflow)
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
-        if (kFast && sizeof(T) == 8) {
+        if (kFast) {
             dydt[3] = f::sub(d3, f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad));
             dydt[4] = f::sub(x4, f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad));
         } else {
@@ -229,7 +229,7 @@ struct Model200 {
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
         T out_grav, out_aq;
-        if (kFast && sizeof(T) == 8) {
+        if (kFast) {
             out_grav = f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad);
             out_aq = f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad);
         } else {
