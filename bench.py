@@ -663,6 +663,11 @@ def main():
                          "traffic_source": "ncu --set full capture of this command (profiles/r1h_ncu_full_window_kernel_10M.csv), per link x links",
                          "peak_source": "measured live: register-resident FMA microbenchmark (hlm_measure_fma_peak); "
                                         "MEASURED_PEAKS.json holds no FP64/FP32 vector peak",
+                         # instruction-level utilisation of the bounding pipe, from the committed ncu capture of this
+                         # command (not measured live: ncu counters are not available inside a timed run)
+                         "fp64_pipe_utilization_ncu": ({"value": 0.615, "metric": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                                                        "source": "profiles/r1h_ncu_full_window_kernel_10M.csv"}
+                                                       if uid == 204 and args.precision == 64 else None),
                          "flop_per_attempt": w_min, "attempts_per_launch": att_per_launch,
                          "kernel_ms_avg": kern_avg_ms, "kernel": f"hlm::rk45_window_kernel<Model{uid},{'double' if args.precision == 64 else 'float'}>",
                          "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
