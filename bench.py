@@ -251,7 +251,7 @@ def run_routed_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)  # never fewer than 3 untimed steps before a timed region (timing rules)
     ns_all = args.links_per_gpu * world
     dt = args.couple_minutes
     n_int = max(1, int(round(60.0 / dt)))
@@ -438,7 +438,7 @@ def main():
         torch.cuda.synchronize()
 
     ns = args.links_per_gpu
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)  # never fewer than 3 untimed steps before a timed region (timing rules)
     assert W + K <= args.days, "not enough forcing days for warmup+steps"
     from tiger_hlm_gpu_b200.sharding import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
