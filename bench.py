@@ -344,7 +344,7 @@ def run_routed_arm(args):
         achieved = W_MIN_FLOP_PER_ATTEMPT_200 * att_per_launch / (kern_avg_ms * 1e-3) / 1e12
         line = {
             "metric": "accepted RK45 system-steps/sec", "value": acc_all / (ms_max * 1e-3), "unit": "accepted system-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "warmup_done": W, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "routed sub-basin network (BASELINE configs[4]): Model 200 (project-defined), synthetic "
                                    "river network, links coupled through upstream discharge held over a coupling interval; "
@@ -648,7 +648,7 @@ def main():
         hbm_gbs = bytes_per_link * ns / (kern_avg_ms * 1e-3) / 1e9
         line = {
             "metric": "accepted RK45 system-steps/sec", "value": value, "unit": "accepted system-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "warmup_done": W, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
             "data": "synthetic", "config": workload_config(args, ns),
             "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),
