@@ -184,6 +184,27 @@ def test_link_chunked_run_is_bit_identical_to_single_window(solver):
     assert_same_result(b, o, exact=True)
 
 
+def test_link_chunked_run_with_optional_outputs_absent(solver):
+    """hlm_run_rk45's outputs other than the dense records may be NULL; in the chunked path each absent one just
+    drops its per-chunk copy."""
+    import ctypes as C
+    ns = 700
+    sp, y0, forcing = setup_synth(solver, ns, 1)
+    tq = synthetic.hourly_queries(0.0, 1440.0)
+    a = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
+    dense = np.zeros((ns, len(tq), 5))
+    acc = np.zeros(ns, np.int64)
+    lib = hlm.load_library()
+    try:
+        solver.set_dense_window_bytes(len(tq) * 5 * 8 * 32 * 4)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        rc = lib.hlm_run_rk45(solver._h, 204, p(y0), ns, 0.0, 1440.0, p(tq), len(tq), None, p(dense), None, p(acc), None, None)
+        assert rc == 0, lib.hlm_last_error().decode()
+    finally:
+        solver.set_dense_window_bytes(8 << 30)
+    assert np.array_equal(dense, a["dense"]) and np.array_equal(acc, a["n_accept"])
+
+
 def test_lane_refill_schedule_is_bit_identical_to_tiles(solver, golden_dummy):
     """hlm_set_schedule: a lane takes the next unclaimed link when it is done with its own instead of waiting for
     its tile.  Same per-link arithmetic, so the same bits — whole run, windowed, link-chunked, DummyModel."""
