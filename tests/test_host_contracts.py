@@ -61,3 +61,18 @@ def test_lookup_mapper(tmp_path):
     assert out[0] == "2" and out[1] == "420555774 1 28 39" and out[2] == "420552129 1 27 40"
     assert out[3] == "5 0 -1 -1"  # {-1,-1} when absent, forcing_loader.cpp:54-60
     assert hostio.load_lookup(str(lk)) == {420555774: (28, 39), 420552129: (27, 40)}
+
+
+def test_parameter_csv_writer_round_trips_through_the_loader(tmp_path):
+    """hostio.write_spatial_params_csv (used to hand synthetic networks to the C++ programs) inverts the loader's
+    unit conversions (I_O/parameters_loader.cpp:57-101) to rounding: topology exactly, parameters to 1e-15."""
+    import numpy as np
+    from tiger_hlm_gpu_b200 import synthetic
+    from tiger_hlm_gpu_b200.hostio import load_spatial_params, write_spatial_params_csv
+    sp = synthetic.apply_network(synthetic.make_spatial_params(50), synthetic.make_network(50, subbasin_links=10))
+    path = str(tmp_path / "p.csv")
+    write_spatial_params_csv(path, sp)
+    back = load_spatial_params(path)
+    assert np.array_equal(back["stream"], sp["stream"]) and np.array_equal(back["next_stream"], sp["next_stream"])
+    for name in ("infil", "perco", "Hu", "n_mann", "slope", "L", "A_h", "alpha3", "alpha4", "melt_f", "temp_thr", "lat"):
+        np.testing.assert_allclose(back[name], sp[name], rtol=1e-15, atol=0)
