@@ -23,8 +23,16 @@ static cudaError_t radau_launch_model(const WindowArgs& a, int* list, unsigned i
     ra.n_list = n_list;
     ra.n_radau = n_radau;
     // the list length lives on the device: a fixed grid strides over it (flagged links are rare)
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((hi - lo + 63) / 64, (long long)sm_count * 4));
-    radau_window_kernel<Model><<<grid, 64, 0, stream>>>(ra);
+#ifndef HLM_RADAU_WARP
+#define HLM_RADAU_WARP 1
+#endif
+    if (HLM_RADAU_WARP) {  // one warp per flagged link
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((hi - lo + 3) / 4, (long long)sm_count * 2));
+        radau_warp_kernel<Model><<<grid, 128, 0, stream>>>(ra);
+    } else {               // one thread per flagged link
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((hi - lo + 63) / 64, (long long)sm_count * 4));
+        radau_window_kernel<Model><<<grid, 64, 0, stream>>>(ra);
+    }
     return cudaGetLastError();
 }
 
