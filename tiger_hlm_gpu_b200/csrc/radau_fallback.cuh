@@ -83,7 +83,7 @@ struct RadauArgs {
 };
 
 // status kStiff -> list (order is arbitrary; every link's result depends on that link alone)
-__global__ void radau_collect_kernel(const int* __restrict__ status, long long lo, long long hi, int* __restrict__ list,
+static __global__ void radau_collect_kernel(const int* __restrict__ status, long long lo, long long hi, int* __restrict__ list,
                                      unsigned int* __restrict__ n_list) {
     const long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < hi && (status[i] == kStiff || status[i] == kStiffPaused)) list[atomicAdd(n_list, 1u)] = (int)i;
