@@ -14,25 +14,47 @@ namespace hlm {
 // schedule 0: tiles (rk45_window_kernel); 1: lane refill; 2: lane refill with the early-leave test (few attempts
 // per link per launch).  The grid is SMs x resident CTAs of the kernel (persistent warps pull work from a
 // counter), fewer when there is less work.
-cudaError_t HLM_INST_NAME(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream) {
-    using Model = HLM_INST_MODEL;
-    using T = HLM_INST_T;
+// a template so that `if constexpr` really leaves the kernels an instance does not carry uninstantiated
+template <class Model, typename T>
+static cudaError_t launch_rk45_impl(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream) {
     static int blocks_per_sm[3] = {0, 0, 0};
     if (schedule < 0 || schedule > 2) return cudaErrorInvalidValue;
-    if (blocks_per_sm[schedule] == 0) {
-        cudaError_t e;
-        if (schedule == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], rk45_window_kernel<Model, T>, HLM_CTA_THREADS, 0);
-        else if (schedule == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], rk45_lanes_kernel<Model, T, false>, HLM_CTA_THREADS, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[2], rk45_lanes_kernel<Model, T, true>, HLM_CTA_THREADS, 0);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm[schedule] < 1) blocks_per_sm[schedule] = 1;
-    }
+    // Which kernels this instance carries (each is minutes of ptxas): lane refill for FP64 only — FP32 has no
+    // routed use (the implicit fallback is FP64) — and its early-leave variant for the models routed runs use
+    // (those with an inflow term).  A schedule the instance lacks falls back to the next simpler one.
+    constexpr bool kHasLanes = sizeof(T) == 8;
+    constexpr bool kHasEarly = kHasLanes && Model::HAS_INFLOW;
+    if (schedule == 2 && !kHasEarly) schedule = 1;
+    if (schedule == 1 && !kHasLanes) schedule = 0;
     constexpr int kWarps = HLM_CTA_THREADS / 32;
-    const long long grid = std::max<long long>(1, std::min<long long>((a.n_tiles + kWarps - 1) / kWarps, (long long)sm_count * blocks_per_sm[schedule]));
-    if (schedule == 0) rk45_window_kernel<Model, T><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
-    else if (schedule == 1) rk45_lanes_kernel<Model, T, false><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
-    else rk45_lanes_kernel<Model, T, true><<<(unsigned)grid, HLM_CTA_THREADS, 0, stream>>>(a);
+    auto grid_for = [&](int bps) {
+        return (unsigned)std::max<long long>(1, std::min<long long>((a.n_tiles + kWarps - 1) / kWarps, (long long)sm_count * bps));
+    };
+    auto occupancy = [&](auto kernel, int slot) -> cudaError_t {
+        if (blocks_per_sm[slot] != 0) return cudaSuccess;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[slot], kernel, HLM_CTA_THREADS, 0);
+        if (e == cudaSuccess && blocks_per_sm[slot] < 1) blocks_per_sm[slot] = 1;
+        return e;
+    };
+    if (schedule == 0) {
+        if (cudaError_t e = occupancy(rk45_window_kernel<Model, T>, 0)) return e;
+        rk45_window_kernel<Model, T><<<grid_for(blocks_per_sm[0]), HLM_CTA_THREADS, 0, stream>>>(a);
+    } else if (schedule == 1) {
+        if constexpr (kHasLanes) {
+            if (cudaError_t e = occupancy(rk45_lanes_kernel<Model, T, false>, 1)) return e;
+            rk45_lanes_kernel<Model, T, false><<<grid_for(blocks_per_sm[1]), HLM_CTA_THREADS, 0, stream>>>(a);
+        }
+    } else {
+        if constexpr (kHasEarly) {
+            if (cudaError_t e = occupancy(rk45_lanes_kernel<Model, T, true>, 2)) return e;
+            rk45_lanes_kernel<Model, T, true><<<grid_for(blocks_per_sm[2]), HLM_CTA_THREADS, 0, stream>>>(a);
+        }
+    }
     return cudaGetLastError();
+}
+
+cudaError_t HLM_INST_NAME(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream) {
+    return launch_rk45_impl<HLM_INST_MODEL, HLM_INST_T>(schedule, a, sm_count, stream);
 }
 
 }  // namespace hlm
