@@ -287,6 +287,7 @@ def test_load_config_reference_schema(io, tmp_path):
         assert cfg[k] == v, k
     # extension keys default so that the reference's file needs no change
     assert cfg["solver.interval"] == "1d" and cfg["output.format"] == "netcdf" and cfg["output.dense"] is True
+    assert cfg["solver.stiff_fallback"] is False and cfg["routing.enabled"] is False and cfg["routing.couple_minutes"] == 15.0
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/data/config.yaml"), reason="reference tree absent")
@@ -312,6 +313,12 @@ def test_load_config_variants_and_errors(io, tmp_path):
     assert cfg["output.states"] == [1, 3] and cfg["output.format"] == "csv" and cfg["output.dense"] is False
     assert cfg["initial.mode"] == "cold" and cfg["initial.file"] == ""
     assert cfg["solver.interval"] == "12h" and cfg["solver.max_attempts"] == 500000
+    # routed runs and the implicit fallback (project extensions)
+    (tmp_path / "routed.yaml").write_text(base.replace("  method: RK45\n", "  method: RK45\n  stiff_fallback: true\n")
+                                          + 'routing:\n  enabled: true\n  couple: "30m"\n  subbasin_links: 512\n')
+    cfg = load_cfg(io, tmp_path / "routed.yaml")
+    assert cfg["solver.stiff_fallback"] is True and cfg["routing.enabled"] is True
+    assert cfg["routing.couple_minutes"] == 30.0 and cfg["routing.subbasin_links"] == 512
     # a missing required key and a malformed time raise (std::runtime_error in the reference)
     (tmp_path / "bad1.yaml").write_text(base.replace("  uid: 204", "  id: 204"))
     assert io.hlmio_load_config_json(str(tmp_path / "bad1.yaml").encode()) is None

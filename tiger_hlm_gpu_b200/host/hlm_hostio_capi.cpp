@@ -124,7 +124,11 @@ const char* hlmio_load_config_json(const char* path) {
               << ",\"solver.atol\":" << c.solver.atol << ",\"solver.safety\":" << c.solver.safety << ",\"solver.min_scale\":" << c.solver.min_scale
               << ",\"solver.max_scale\":" << c.solver.max_scale << ",\"solver.override_initial_step\":" << (c.solver.override_initial_step ? "true" : "false")
               << ",\"solver.initial_step\":" << c.solver.initial_step << ",\"solver.interval\":\"" << json_escape(c.solver.interval) << "\""
-              << ",\"solver.max_attempts\":" << c.solver.max_attempts << ",\"mpi.step_storage\":" << c.mpi.step_storage
+              << ",\"solver.max_attempts\":" << c.solver.max_attempts
+              << ",\"solver.stiff_fallback\":" << (c.solver.stiff_fallback ? "true" : "false")
+              << ",\"routing.enabled\":" << (c.routing.enabled ? "true" : "false") << ",\"routing.couple\":\"" << json_escape(c.routing.couple) << "\""
+              << ",\"routing.couple_minutes\":" << parse_interval_minutes(c.routing.couple)
+              << ",\"routing.subbasin_links\":" << c.routing.subbasin_links << ",\"mpi.step_storage\":" << c.mpi.step_storage
               << ",\"mpi.transfer_buffer\":" << c.mpi.transfer_buffer << ",\"mpi.discontinuity_buf\":" << c.mpi.discontinuity_buf
               << ",\"flags.uses_dam\":" << (c.flags.uses_dam ? "true" : "false") << ",\"flags.convert_area\":" << (c.flags.convert_area ? "true" : "false") << "}";
             g_text = o.str();
