@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -759,6 +760,30 @@ static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, double* dens
         a.forc_dt_min[j] = c->forc_dt_h[j] * 60.0;  // rk45_kernel.cu:90
     }
     a.forc_ncols = c->forc_ncols;
+    {   // the samples every link starts the launch with, when they all start at t0 (LinkRun::load); the same
+        // expressions as the device's forcing_index, in IEEE double on both sides
+        const ModelInfo* mi = find_model(c->uid);
+        const int nf = mi ? std::min(std::min(c->n_forc, mi->n_forc), 2) : 0;
+        double lo = -INFINITY, hi = INFINITY;
+        bool ok = nf > 0;
+        for (int j = 0; j < nf && ok; ++j) {
+            const double dtm = a.forc_dt_min[j];
+            const long long nT = a.forc_nT[j];
+            if (!(dtm > 0.0) || nT <= 0) { ok = false; break; }
+            const double r = c->t0 / dtm;
+            const long long idx = (r < 0.0) ? 0 : ((r >= (double)nT) ? nT - 1 : (long long)r);
+            const double l = (idx <= 0) ? -INFINITY : (double)idx * dtm * (1.0 + 1e-9);
+            const double h = (idx >= nT - 1) ? INFINITY : (double)(idx + 1) * dtm * (1.0 - 1e-9);
+            long long row = idx - a.forc_i0[j];
+            row = row < 0 ? 0 : (row >= a.forc_nres[j] ? a.forc_nres[j] - 1 : row);
+            a.forc_pre_row[j] = row;
+            lo = std::max(lo, l);
+            hi = std::min(hi, h);
+        }
+        a.forc_pre_ok = ok ? 1 : 0;
+        a.forc_pre_lo = lo;
+        a.forc_pre_hi = hi;
+    }
     a.tq = c->tq.p;
     a.nq = (int)c->nq;
     a.q_lo = (int)q_lo;

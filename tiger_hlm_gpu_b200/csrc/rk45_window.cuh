@@ -164,6 +164,12 @@ struct WindowArgs {
     const double* qin;     // [ld]
     const int* send_slot;  // [ld] or nullptr
     double* send_buf;
+    // Forcing samples of the launch's start time, worked out once on the host (same arithmetic as forcing_index):
+    // a link whose own time lies in [forc_pre_lo, forc_pre_hi) takes rows forc_pre_row[j] without recomputing
+    // the index — in routed runs every link is (re)loaded every coupling interval, all at the same time.
+    int forc_pre_ok;
+    long long forc_pre_row[2];
+    double forc_pre_lo, forc_pre_hi;
     // peer-memory exchange (one process per GPU on one node): instead of a send buffer a collective then moves,
     // the discharge is stored straight into every rank's halo vector through its IPC-mapped address, element
     // peer_off + slot (peer_off = parity * halo length + my rank * segment length); nullptr = not in use
@@ -387,7 +393,17 @@ template <class Model, typename T> struct LinkRun {
         col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
         F[0] = F[1] = (T)0;
         f_lo = fp<double>::inf();
-        f_hi = -fp<double>::inf();  // empty validity interval
+        f_hi = -fp<double>::inf();  // empty validity interval: the first attempt looks the samples up
+        if (Model::N_FORC > 0 && a.n_forc > 0 && a.forc_pre_ok) {
+            const double td = (double)t;
+            if (td >= a.forc_pre_lo && td < a.forc_pre_hi) {  // the launch-level lookup holds for this link
+#pragma unroll
+                for (int j = 0; j < Model::N_FORC; ++j)
+                    if (j < a.n_forc) F[j] = (T)__ldg(a.forc[j] + a.forc_pre_row[j] * a.forc_ncols + col);
+                f_lo = a.forc_pre_lo;
+                f_hi = a.forc_pre_hi;
+            }
+        }
         tq_next = (next_q < a.nq) ? (T)__ldg(a.tq + next_q) : f::inf();
         k0_valid = false;
         budget = (a.max_attempts > 0x7fffffffLL) ? 0x7fffffff : (int)a.max_attempts;
