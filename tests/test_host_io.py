@@ -327,3 +327,24 @@ def test_load_config_variants_and_errors(io, tmp_path):
     assert io.hlmio_load_config_json(str(tmp_path / "bad2.yaml").encode()) is None
     assert io.hlmio_last_error() == b"Failed to parse time: January first"
     assert io.hlmio_load_config_json(str(tmp_path / "absent.yaml").encode()) is None
+
+
+def test_interval_boundaries_always_advance(io):
+    """hlm_run's interval loop (hlm_run.cpp) with intervals that are not a whole number of minutes: the boundary
+    after k*interval must be (k+1)*interval, never k*interval again (floor(ta/interval) can round just below k)."""
+    io.hlmio_interval_boundaries.restype = C.c_longlong
+    io.hlmio_interval_boundaries.argtypes = [C.c_double, C.c_double, C.c_char_p, C.c_void_p, C.c_longlong]
+    for text, minutes in (("10s", 10.0 / 60.0), ("20s", 20.0 / 60.0), ("0.1m", 0.1), ("0.7", 0.7), ("1h", 60.0), ("15", 15.0)):
+        t0, t1 = 0.0, minutes * 500.25
+        out = np.zeros(2048)
+        n = io.hlmio_interval_boundaries(t0, t1, text.encode(), _p(out), out.size)
+        assert n == 501, (text, n, io.hlmio_last_error().decode())
+        b = out[:n]
+        assert np.all(np.diff(np.concatenate([[t0], b])) > 0)
+        assert b[-1] == t1
+        np.testing.assert_allclose(b[:-1], minutes * np.arange(1, 501), rtol=1e-12)
+    # a start inside an interval, and one exactly on a boundary
+    out = np.zeros(8)
+    assert io.hlmio_interval_boundaries(90.0, 200.0, b"1h", _p(out), 8) == 3 and list(out[:3]) == [120.0, 180.0, 200.0]
+    assert io.hlmio_interval_boundaries(120.0, 240.0, b"1h", _p(out), 8) == 2 and list(out[:2]) == [180.0, 240.0]
+    assert io.hlmio_interval_boundaries(0.0, 10.0, b"0", _p(out), 8) == -1

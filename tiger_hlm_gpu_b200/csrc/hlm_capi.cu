@@ -199,6 +199,8 @@ __global__ void prepare_params_kernel(const unsigned char* __restrict__ aos, lon
         for (int c = 0; c < Model::N_SP; ++c) out[c] = 1.0;  // padding lanes are never integrated
     }
     for (int c = 0; c < Model::N_SP; ++c) soa[(long long)c * ld + i] = out[c];
+    if (Model::kWetStride > 0)  // the surface branch's parameters as one record per link (models.cuh, wet_block)
+        Model::prepare_wet(out, soa + (long long)Model::N_SP * ld + i * Model::kWetStride);
 }
 
 // links [lo, hi) of the padded range (hi may reach ld: padding lanes are parked as done)
@@ -307,9 +309,9 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
     case 2: r = __ddiv_rn(x[i], y[i]); break;
     case 3: r = __dsqrt_rn(x[i]); break;
     case 4: {  // the kernels' fast pow with its fallback, as the solver uses it
-        bool bad = false;
-        r = hlm::fp<double>::pow_pos<true>(x[i], y[i], bad);
-        if (bad) r = hlm::fp<double>::pow_pos<false>(x[i], y[i], bad);
+        hlm::fp<double>::guard g;
+        r = hlm::fp<double>::pow_pos<true>(x[i], y[i], g);
+        if (g.failed()) r = hlm::fp<double>::pow_pos<false>(x[i], y[i], g);
         break;
     }
     default: r = 0.0;
@@ -352,7 +354,7 @@ template <class Model> int prepare_params(hlm_ctx* c) {
     if (c->sp_n != c->ns)
         return fail(HLM_ERR_STATE, "model needs per-link parameters: upload exactly ns SpatialParams records first");
     if (c->sp_soa_uid == Model::UID && c->sp_soa_ld == ld) return 0;
-    HLM_CUDA(c->sp_soa.reserve((size_t)Model::N_SP * ld));
+    HLM_CUDA(c->sp_soa.reserve((size_t)(Model::N_SP + Model::kWetStride) * ld));
     const int tpb = 256;
     prepare_params_kernel<Model><<<(unsigned)((ld + tpb - 1) / tpb), tpb, 0, c->stream>>>(
         c->sp_aos.p, c->sp_n, (long long)sizeof(hlm::SpatialParamsAoS), c->sp_soa.p, ld);

@@ -41,6 +41,17 @@ struct Model204 {
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };  // R_* = fp<double>::div_recip of the divisor
 
+    // wet_block: the surface branch's five parameters as one 64-byte record per link, stored behind the N_SP
+    // columns of the prepared-parameter buffer (total (N_SP + kWetStride) * ld doubles)
+    static constexpr int kWetStride = 8;
+    static __host__ __device__ constexpr int wet_slot(int c) {
+        return c == INV_N ? 0 : c == SQRT_SLOPE ? 1 : c == LEN ? 2 : c == A_H ? 3 : 4 /* R_A_H */;
+    }
+    static __device__ __forceinline__ void prepare_wet(const double* out, double* rec) {
+        rec[0] = out[INV_N]; rec[1] = out[SQRT_SLOPE]; rec[2] = out[LEN]; rec[3] = out[A_H]; rec[4] = out[R_A_H];
+        rec[5] = rec[6] = rec[7] = 0.0;
+    }
+
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS& s, double* out) {
         out[INFIL] = s.infil;
         out[PERCO] = s.perco;
@@ -62,32 +73,32 @@ struct Model204 {
         out[R_ALPHA4] = (s.alpha4 >= 1.0) ? fp<double>::div_recip(s.alpha4) : 0.0;
     }
 
-    // Per-link constants held in registers for a whole window.  The five columns only the surface
+    // Per-link constants held in registers for a whole window.  The five parameters only the surface
     // (h_surf != 0) branch reads — INV_N, SQRT_SLOPE, LEN, A_H, R_A_H — are NOT kept: that branch
     // re-reads them through the read-only path (L1 hits), which frees 10 registers on a kernel that
-    // sits at the 168-register cap of 3 CTAs/SM.
+    // sits at the 168-register cap of 3 CTAs/SM.  They come from a 64-byte record per link behind the
+    // columns (wet_block), so the branch needs ONE address and immediate offsets: with five column
+    // addresses the compiler rebuilt all five on every attempt, dry or not (16 instructions, 10 registers).
     template <typename T> struct Link {
         T p[N_SP];  // wet-only slots stay unused (dead registers are eliminated)
-        const double* wet;  // &sp[0][sys]
-        long long ld;
+        const double* wet;  // the link's record {INV_N, SQRT_SLOPE, LEN, A_H, R_A_H, -, -, -}
         bool recips_ok;
         __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld_, long long sys) {
             const int dry[] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, MELT_F, TEMP_THR, R_HU, R_ALPHA3, R_ALPHA4};
 #pragma unroll
             for (int i = 0; i < 10; ++i) p[dry[i]] = (T)__ldg(sp + (long long)dry[i] * ld_ + sys);
-            wet = sp + sys;
-            ld = ld_;
+            wet = sp + (long long)N_SP * ld_ + sys * kWetStride;
             const double ra = __ldg(sp + (long long)R_A_H * ld_ + sys);
             recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
         }
-        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + (long long)c * ld); }
+        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + wet_slot(c)); }
     };
 
     /// true when every hoisted reciprocal is usable (divisors inside div_recip's exponent range)
     template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) { return P.recips_ok; }
 
-    template <typename T, bool kFast>
-    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, bool& bad) {
+    template <typename T, bool kFast, typename G>
+    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, G& bad) {
         using f = fp<T>;
         const T h_snow = y[0], h_stat = y[1], h_surf = y[2], h_grav = y[3], h_aq = y[4];
         const T rainfall = F[0], temperature = F[1];
@@ -98,7 +109,7 @@ struct Model204 {
         dydt[0] = f::sub(rainfall, snowmelt);
 
         // 2) static
-        const T x2 = f::max_a((T)0, f::sub(f::add(x1, h_stat), P.p[HU]));
+        const T x2 = f::max0(f::sub(f::add(x1, h_stat), P.p[HU]));
         const T d1 = f::sub(x1, x2);
         const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
         const T s = f::template div_by<kFast>(h_stat, P.p[HU], P.p[R_HU], bad);
@@ -122,7 +133,7 @@ struct Model204 {
         // 4) gravitational (interflow), 5) aquifer (baseflow)
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
-        if (kFast) {
+        if constexpr (kFast) {
             dydt[3] = f::sub(d3, f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad));
             dydt[4] = f::sub(x4, f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad));
         } else {
@@ -155,6 +166,17 @@ struct Model200 {
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, CH, INVTAU,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };
 
+    // wet_block: the surface branch's five parameters as one 64-byte record per link, stored behind the N_SP
+    // columns of the prepared-parameter buffer (total (N_SP + kWetStride) * ld doubles)
+    static constexpr int kWetStride = 8;
+    static __host__ __device__ constexpr int wet_slot(int c) {
+        return c == INV_N ? 0 : c == SQRT_SLOPE ? 1 : c == LEN ? 2 : c == A_H ? 3 : 4 /* R_A_H */;
+    }
+    static __device__ __forceinline__ void prepare_wet(const double* out, double* rec) {
+        rec[0] = out[INV_N]; rec[1] = out[SQRT_SLOPE]; rec[2] = out[LEN]; rec[3] = out[A_H]; rec[4] = out[R_A_H];
+        rec[5] = rec[6] = rec[7] = 0.0;
+    }
+
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS& s, double* out) {
         out[INFIL] = s.infil;
         out[PERCO] = s.perco;
@@ -178,33 +200,31 @@ struct Model200 {
     template <typename T> struct Link {
         T p[N_SP];
         T qin;
-        const double* wet;
-        long long ld;
+        const double* wet;  // the link's wet_block record (see Model204::Link)
         bool recips_ok;
         __device__ __forceinline__ void load(const double* __restrict__ sp, long long ld_, long long sys) {
             const int dry[] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, CH, INVTAU, R_HU, R_ALPHA3, R_ALPHA4};
 #pragma unroll
             for (int i = 0; i < 10; ++i) p[dry[i]] = (T)__ldg(sp + (long long)dry[i] * ld_ + sys);
-            wet = sp + sys;
-            ld = ld_;
+            wet = sp + (long long)N_SP * ld_ + sys * kWetStride;
             qin = (T)0;
             const double ra = __ldg(sp + (long long)R_A_H * ld_ + sys);
             recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
         }
         __device__ __forceinline__ void set_inflow(T v) { qin = v; }
-        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + (long long)c * ld); }
+        __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + wet_slot(c)); }
     };
 
     template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) { return P.recips_ok; }
 
-    template <typename T, bool kFast>
-    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, bool& bad) {
+    template <typename T, bool kFast, typename G>
+    static __device__ __forceinline__ void rhs(const T* y, const T* F, const Link<T>& P, T* dydt, G& bad) {
         using f = fp<T>;
         const T q = y[0], h_stat = y[1], h_surf = y[2], h_grav = y[3], h_aq = y[4];
         const T rainfall = F[0], temperature = F[1];
 
         // static store (Model204 without snow: x1 = rainfall)
-        const T x2 = f::max_a((T)0, f::sub(f::add(rainfall, h_stat), P.p[HU]));
+        const T x2 = f::max0(f::sub(f::add(rainfall, h_stat), P.p[HU]));
         const T d1 = f::sub(rainfall, x2);
         const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
         const T s = f::template div_by<kFast>(h_stat, P.p[HU], P.p[R_HU], bad);
@@ -229,7 +249,7 @@ struct Model200 {
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
         T out_grav, out_aq;
-        if (kFast) {
+        if constexpr (kFast) {
             out_grav = f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad);
             out_aq = f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad);
         } else {
@@ -260,13 +280,15 @@ struct DummyModel {
     static constexpr int N_SP = 0;
     static constexpr int N_FORC = 0;
     static constexpr bool HAS_INFLOW = false;
+    static constexpr int kWetStride = 0;
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS&, double*) {}
+    static __device__ __forceinline__ void prepare_wet(const double*, double*) {}
     template <typename T> struct Link {
         __device__ __forceinline__ void load(const double*, long long, long long) {}
     };
     template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>&) { return true; }
-    template <typename T, bool kFast>
-    static __device__ __forceinline__ void rhs(const T* y, const T*, const Link<T>&, T* dydt, bool&) {
+    template <typename T, bool kFast, typename G>
+    static __device__ __forceinline__ void rhs(const T* y, const T*, const Link<T>&, T* dydt, G&) {
         using f = fp<T>;
         const T Y0 = f::mul((T)0.5, y[0]);
         const T X2 = f::mul((T)0.3, y[1]);

@@ -198,10 +198,10 @@ struct StepOut {
 
 // One DOPRI5 attempt from (y, k0): fills k[1..6], y_next and the FSAL flag, returns err.
 // solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
-template <class Model, typename T, bool kFast>
+template <class Model, typename T, bool kFast, typename G>
 __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][Model::N_EQ], T h,
                                            const T* F, const typename Model::template Link<T>& L, T rtol, T atol,
-                                           T (&y_next)[Model::N_EQ], bool& fsal, bool& bad) {
+                                           T (&y_next)[Model::N_EQ], bool& fsal, G& bad) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     const auto& TB = dp::tab<T>::get();
@@ -244,9 +244,31 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
         const T ymax = f::max_a(f::abs(y[i]), f::abs(y_next[i]));  // y NaN => y_next NaN: same result as fmax
         const T tol = f::fma(rtol, ymax, atol);
         const T ratio = f::abs(f::template div_err<kFast>(e, tol, bad));
-        if (ratio > max_ratio) max_ratio = ratio;  // NaN-ignoring form of the reference
+        // NaN-ignoring form of the reference: if (ratio > max_ratio) max_ratio = ratio, from 0
+        if (i == 0) max_ratio = f::max0(ratio);
+        else if (ratio > max_ratio) max_ratio = ratio;
     }
     return max_ratio;
+}
+
+// The exact attempt (real div.rn / rcp.rn / libdevice pow), for the rare attempt whose operands leave the domain
+// of the fast forms.  Out of line on copies of the lane's state in local memory: the hot loop then holds one
+// attempt, not two, which halves its instruction footprint (the L1.5 instruction cache is 32 KB, the two bodies
+// together were 78 KB) and leaves the register allocation of the fast path without a second producer per value.
+template <class Model, typename T> struct ExactIO {
+    T y[Model::N_EQ], k[7][Model::N_EQ], y_next[Model::N_EQ], F[2];
+    T h, err, fac0;
+    typename Model::template Link<T> L;
+    bool fsal;
+};
+template <class Model, typename T>
+__device__ __noinline__ void exact_attempt(ExactIO<Model, T>& io, T rtol, T atol, T safety) {
+    using f = fp<T>;
+    bool unused = false, fsal = false;
+    Model::template rhs<T, false>(io.y, io.F, io.L, io.k[0], unused);  // rk45_kernel.cu:114
+    io.err = dopri_attempt<Model, T, false>(io.y, io.k, io.h, io.F, io.L, rtol, atol, io.y_next, fsal, unused);
+    io.fac0 = f::mul(safety, f::template pow_pos<false>(f::rcp(f::add(io.err, (T)1e-16)), (T)0.2, unused));
+    io.fsal = fsal;
 }
 
 // Exact forcing sample index of the reference (rk45_kernel.cu:90-98) plus a conservative interval
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
         typename Model::template Link<T> L;
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
-        const bool fast_ok = Model::template fast_div_ok<T>(L);
+        const bool fast_ok = Model::template fast_div_ok<T>(L) && f::fast_params_ok(rtol, atol);
         const long long col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
 
         T F[2] = {(T)0, (T)0};
@@ -389,7 +411,7 @@ template <class Model, typename T> struct LinkRun {
         n_jmp = a.n_jump[sys];
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
-        fast_ok = Model::template fast_div_ok<T>(L);
+        fast_ok = Model::template fast_div_ok<T>(L) && f::fast_params_ok((T)a.prm.rtol, (T)a.prm.atol);
         col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
         F[0] = F[1] = (T)0;
         f_lo = fp<double>::inf();

@@ -19,6 +19,7 @@
 //                              in coupling intervals, upstream discharge held over each
 #pragma once
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -283,6 +284,19 @@ inline double parse_interval_minutes(const std::string& s) {
     if (unit == "h") return v * 60.0;
     if (unit == "d") return v * 1440.0;
     throw std::runtime_error("config: bad interval unit in '" + s + "'");
+}
+
+/// End of the solver interval that starts at `ta`: the next multiple of `interval` (minutes from the origin)
+/// strictly after ta, capped at t_end.  Multiples are counted with an integer — ta / interval can round just
+/// below k once ta = k * interval when the interval is not a whole number of minutes (10s, 0.1m), and
+/// floor(ta / interval) + 1 then returns ta itself for ever.  `k` carries the count between calls (start at 0).
+inline double next_interval_boundary(double ta, double t_end, double interval, long long& k) {
+    if (!(interval > 0.0)) throw std::runtime_error("config: interval must be positive");
+    if (k <= 0) k = (long long)std::floor(ta / interval + 1e-9) + 1;
+    while ((double)k * interval <= ta) ++k;
+    const double tb = std::min(t_end, (double)k * interval);
+    if (!(tb > ta)) throw std::runtime_error("config: interval boundary does not advance (interval too small for the time axis)");
+    return tb;
 }
 
 namespace hlmcfg_detail {

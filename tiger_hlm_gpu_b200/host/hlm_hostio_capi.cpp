@@ -48,6 +48,21 @@ int hlmio_inquire(const char* path, const char* var, long long* shape, int* elem
     });
     return rc ? -1 : rank;
 }
+/// the solver intervals hlm_run cuts [t_begin, t_end] into: fills bounds[0..n] (at most cap), returns n or -1
+long long hlmio_interval_boundaries(double t_begin, double t_end, const char* interval, double* bounds, long long cap) {
+    long long n = 0;
+    const int rc = guarded([&] {
+        const double dt = parse_interval_minutes(interval);
+        long long k = 0;
+        for (double ta = t_begin; ta < t_end;) {
+            const double tb = next_interval_boundary(ta, t_end, dt, k);
+            if (n < cap) bounds[n] = tb;
+            ++n;
+            ta = tb;
+        }
+    });
+    return rc ? -1 : n;
+}
 /// newline-separated variable names
 const char* hlmio_variables(const char* path) {
     g_text.clear();

@@ -313,8 +313,9 @@ int run(const Options& opt) {
     size_t q_next = 0;  // first query not yet assigned to an interval
     bool first = true;
     int slot = 0;
+    long long k_int = 0;  // interval counter of next_interval_boundary (hlm_config.hpp)
     for (double ta = t_begin; ta < t_end;) {
-        const double tb = std::min(t_end, (std::floor(ta / interval) + 1.0) * interval);  // boundaries at multiples of the interval from the origin
+        const double tb = next_interval_boundary(ta, t_end, interval, k_int);  // multiples of the interval from the origin
         size_t q_end = q_next;
         while (q_end < tq.size() && tq[q_end] <= tb) ++q_end;
         const long long nq = (long long)(q_end - q_next);
