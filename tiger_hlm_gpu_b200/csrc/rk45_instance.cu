@@ -2,6 +2,7 @@
 // its launcher.  Compiled once per instance (Makefile: -DHLM_INST_MODEL=... -DHLM_INST_T=... -DHLM_INST_NAME=...)
 // so that the instances build in parallel; hlm_capi.cu only sees the launchers.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rk45_window.cuh"
 
@@ -27,7 +28,13 @@ static cudaError_t launch_rk45_impl(int schedule, const WindowArgs& a, int sm_co
     if (schedule == 2 && !kHasEarly) schedule = 1;
     if (schedule == 1 && !kHasLanes) schedule = 0;
     constexpr int kWarps = HLM_CTA_THREADS / 32;
+    // HLM_TUNE_BLOCKS_PER_SM (environment): cap on resident CTAs per SM, for occupancy experiments only
+    static const int bps_cap = [] {
+        const char* e = std::getenv("HLM_TUNE_BLOCKS_PER_SM");
+        return e ? std::max(1, std::atoi(e)) : 1 << 20;
+    }();
     auto grid_for = [&](int bps) {
+        bps = std::min(bps, bps_cap);
         return (unsigned)std::max<long long>(1, std::min<long long>((a.n_tiles + kWarps - 1) / kWarps, (long long)sm_count * bps));
     };
     auto occupancy = [&](auto kernel, int slot) -> cudaError_t {
