@@ -91,8 +91,10 @@ int hlm_get_model_parameters(hlm_ctx* ctx, int uid, double p[6]);
 /* Replaces the cudaMalloc/cudaMemcpy of the AoS SpatialParams array (main.cpp:392-404) and, across
  * GPUs, the MPI rank-0 scatter of its row chunks (main.cpp:269-309,357-366): the caller hands each
  * device context its own contiguous slice.  `aos` points at `n` records `stride_bytes` apart, each
- * laid out as the reference's 136-byte SpatialParams (I_O/parameters_loader.hpp:19-37).  The
- * records are transposed on the device into the structure-of-arrays columns each model needs. */
+ * laid out as the reference's 136-byte SpatialParams (I_O/parameters_loader.hpp:19-37), in HOST memory
+ * or in DEVICE memory (the d_sp the reference's run_rk45 receives, solver/rk45_api.hpp:279; the copy
+ * direction is taken from the pointer).  The records are transposed on the device into the
+ * structure-of-arrays columns each model needs. */
 int hlm_upload_spatial_params(hlm_ctx* ctx, const void* aos, long long n, long long stride_bytes);
 
 /* Replaces the forcing side channel: d_forc_data upload plus cudaMemcpyToSymbol of c_forc_dt /
@@ -139,6 +141,20 @@ int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
 int hlm_set_schedule(hlm_ctx* ctx, int mode);
 /* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */
 int hlm_set_precision(hlm_ctx* ctx, int bits);
+/* Which states a dense record carries: bit i of `mask` = state i of the model, records hold the selected states
+ * in ascending order; 0 (default) = all N_EQ states, the reference's layout.  This is config.yaml's
+ * `output.states` (data/config.yaml, main.cpp:788-793) applied where the records are produced: the window kernel
+ * interpolates and stores only the selected states, so a discharge-only run of Model 200 moves a fifth of the
+ * bytes over PCIe.  Every dense buffer of the ABI (hlm_run_rk45's out_dense, hlm_solve_fetch_window*, the device
+ * window buffer) then is [ns][nq][n_selected].  Final states are always all N_EQ.  Takes effect for windows
+ * queued after the call. */
+int hlm_set_output_states(hlm_ctx* ctx, unsigned int mask);
+/* Dense records as double (64, default: the reference's type, I_O/output_series.cpp:88-123) or float (32): the
+ * states are integrated in the solver's precision and rounded once when the record is stored.  Halves the output
+ * bytes; an archive type, like NetCDF's own NC_FLOAT packing.  Dense buffers then hold float. */
+int hlm_set_output_precision(hlm_ctx* ctx, int bits);
+/* Columns per dense record and bytes per value for model `uid` under the current two settings. */
+int hlm_output_layout(hlm_ctx* ctx, int uid, int* n_columns, int* bytes_per_value);
 
 /* ---- the operator ---------------------------------------------------------------------------- */
 
@@ -150,14 +166,15 @@ int hlm_set_precision(hlm_ctx* ctx, int bits);
  *   tq          host [nq] ascending query times (may be NULL when nq == 0)
  *   out_final   host [ns][N_EQ]; rows of links that did not reach tf are zero (the reference
  *               leaves them unwritten, solver/rk45_kernel.cu:167-175)
- *   out_dense   host [ns][nq][N_EQ] — the order retrieve_and_free returns
+ *   out_dense   host [ns][nq][N_EQ] doubles — the order retrieve_and_free returns
  *               (solver/rk45_api.hpp:255-267); slots never reached (tq <= t0, or after a stiff
- *               bail-out) are zero.  May be NULL.
+ *               bail-out) are zero.  May be NULL.  With hlm_set_output_states / hlm_set_output_precision:
+ *               [ns][nq][n_selected] of double or float (hlm_output_layout).
  *   out_stiff   host [ns] HLM_LINK_* codes.  May be NULL.
  *   out_n_*     host [ns] accepted / rejected / slope-jump attempt counts.  May be NULL.
  * ns must equal the number of uploaded SpatialParams records for models that use them. */
 int hlm_run_rk45(hlm_ctx* ctx, int uid, const double* y0, long long ns, double t0, double tf,
-                 const double* tq, long long nq, double* out_final, double* out_dense, int* out_stiff,
+                 const double* tq, long long nq, double* out_final, void* out_dense, int* out_stiff,
                  long long* out_n_accept, long long* out_n_reject, long long* out_n_jump);
 
 /* ---- resident session: the same operator cut into output windows, state left in HBM ---------- */
@@ -185,13 +202,13 @@ int hlm_solve_window(hlm_ctx* ctx, long long q_hi, int want_dense);
 int hlm_solve_window_buffer(hlm_ctx* ctx, void** dev_ptr, long long* q_lo, long long* q_hi);
 /* Copy the last window's dense records into the full host array [ns][nq][N_EQ]. Asynchronous if
  * `host_dense` is pinned. */
-int hlm_solve_fetch_window(hlm_ctx* ctx, double* host_dense);
+int hlm_solve_fetch_window(hlm_ctx* ctx, void* host_dense);
 /* Copy the last window's dense records packed as [ns][q_hi - q_lo][N_EQ] (the feed of a windowed file
  * writer).  Asynchronous on the copy stream if `host_win` is pinned; `ticket` (may be NULL) names the
  * copy for hlm_solve_wait_copy(), which blocks until that copy has landed (ticket < 0: all queued
  * copies) and may be called from another host thread.  The reference copies the whole dense array with
  * one blocking cudaMemcpy after the run (solver/rk45_api.hpp:173-196). */
-int hlm_solve_fetch_window_packed(hlm_ctx* ctx, double* host_win, int* ticket);
+int hlm_solve_fetch_window_packed(hlm_ctx* ctx, void* host_win, int* ticket);
 int hlm_solve_wait_copy(hlm_ctx* ctx, int ticket);
 /* Page-locked host memory for those copies (cudaHostAlloc / cudaFreeHost without linking the CUDA
  * runtime into the host program). */

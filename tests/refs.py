@@ -35,7 +35,7 @@ def ref_cuda():
     return _cuda
 
 
-def ref_cuda_run204(prm6, y0, t0, tf, tq, sp, forc_blocks, dt_hours, counted=True):
+def ref_cuda_run204(prm6, y0, t0, tf, tq, sp, forc_blocks, dt_hours, counted=True, want_dense=True):
     """Run the reference kernel.  forc_blocks: list of float32 [nT][ns] (per-link expanded)."""
     y0 = np.ascontiguousarray(y0, np.float64).reshape(-1, 5)
     ns = y0.shape[0]
@@ -49,7 +49,7 @@ def ref_cuda_run204(prm6, y0, t0, tf, tq, sp, forc_blocks, dt_hours, counted=Tru
     dt = np.array(list(dt_hours) or [1.0], np.float64)
     prm = np.ascontiguousarray(prm6, np.float64)
     final = np.zeros((ns, 5))
-    dense = np.zeros((ns, max(nq, 1), 5))
+    dense = np.zeros((ns, max(nq, 1), 5)) if want_dense else None  # None: timing runs skip the 40*nq bytes/link round trip
     stiff = np.zeros(ns, np.int32)
     att, eok, jmp = (np.zeros(ns, np.int32) for _ in range(3))
     ms = C.c_float()
@@ -58,7 +58,7 @@ def ref_cuda_run204(prm6, y0, t0, tf, tq, sp, forc_blocks, dt_hours, counted=Tru
                                     _p(eok), _p(jmp), C.addressof(ms))
     if rc != 0:
         raise RuntimeError(f"ref_cuda_run204 failed rc={rc}")
-    out = dict(final=final, dense=dense[:, :nq], stiff=stiff, kernel_ms=ms.value)
+    out = dict(final=final, dense=dense[:, :nq] if dense is not None else None, stiff=stiff, kernel_ms=ms.value)
     if counted:
         out.update(n_accept=(eok - jmp).astype(np.int64), n_reject=(att - eok).astype(np.int64),
                    n_jump=jmp.astype(np.int64))

@@ -109,3 +109,27 @@ def test_cpp_routed_nccl_two_processes(tmp_path):
     fin_g = np.array([got[int(s)] for s in sp["stream"]])
     assert np.array_equal(fin_g, fin_o)
     assert routing.plan(sp["stream"], sp["next_stream"], world, subbasin_links=sub).n_cut_edges > 0
+
+
+def test_reference_call_sequence_compiles_and_runs_against_the_shim(golden204):
+    """host/refcall_selftest.cpp: setup_gpu_buffers -> launch_rk45_kernel -> retrieve_and_free with the reference's
+    names, tuple shape and argument order (main.cpp:666-732, solver/rk45_api.hpp:63-270), then run_rk45 with the
+    reference's signature on a cudaMalloc'ed d_sp (main.cpp:392-404); the program itself checks that both give the
+    same bits, here the printed final state is checked against the reference's golden."""
+    exe = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host", "build", "hlm_refcall_selftest")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "small_test.csv")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("refcall ok: 10 systems, 49 queries")
+    got = np.array([float(x) for x in r.stdout.split("=")[1].split()])
+    want = golden204["final"][0]
+    assert np.all(np.abs(got - want) <= 10 * (1e-9 + 1e-6 * np.abs(want)) + 1e-8 * np.abs(want))
+
+
+def test_shim_bench_program_reports_throughput():
+    """host/bench_shim.cpp (bench.py's e2e_shim record) on a small case: pooled page-locked result vectors."""
+    import json
+    exe = os.path.join(ROOT, "tiger_hlm_gpu_b200", "host", "build", "hlm_bench_shim")
+    r = subprocess.run([exe, "20000", "2", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["links"] == 20000 and d["steps"] == 2 and d["value"] > 1e6 and np.isfinite(d["checksum"])

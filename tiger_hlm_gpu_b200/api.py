@@ -15,7 +15,7 @@ from dataclasses import dataclass, astuple
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -51,6 +51,9 @@ SIGNATURES = {
     "hlm_set_max_attempts": (_I, [_V, _LL]),
     "hlm_set_dense_window_bytes": (_I, [_V, _LL]),
     "hlm_set_precision": (_I, [_V, _I]),
+    "hlm_set_output_states": (_I, [_V, C.c_uint]),
+    "hlm_set_output_precision": (_I, [_V, _I]),
+    "hlm_output_layout": (_I, [_V, _I, C.POINTER(_I), C.POINTER(_I)]),
     "hlm_set_schedule": (_I, [_V, _I]),
     "hlm_set_stiff_fallback": (_I, [_V, _I]),
     "hlm_solve_radau_steps": (_I, [_V, _V]),
@@ -256,6 +259,24 @@ class Solver:
     def set_precision(self, bits: int):
         _check(self._lib.hlm_set_precision(self._h, bits))
 
+    def set_output_states(self, states=None):
+        """config.yaml's output.states applied on the device: dense records carry only these state indices
+        (ascending).  None / empty = all states (the reference's layout)."""
+        mask = 0
+        for i in (states or []):
+            mask |= 1 << int(i)
+        _check(self._lib.hlm_set_output_states(self._h, mask))
+
+    def set_output_precision(self, bits: int):
+        """Dense records as float64 (default, the reference's type) or float32."""
+        _check(self._lib.hlm_set_output_precision(self._h, bits))
+
+    def output_layout(self, uid: int):
+        """(columns per dense record, numpy dtype of a value) under the current output settings."""
+        n, b = _I(), _I()
+        _check(self._lib.hlm_output_layout(self._h, uid, C.byref(n), C.byref(b)))
+        return n.value, (np.float32 if b.value == 4 else np.float64)
+
     # -- the operator ----------------------------------------------------------------------------
     def run_rk45(self, uid: int, y0, t0: float, tf: float, tq, want_dense=True, out_final=None, out_dense=None):
         """hlm_run_rk45 with host buffers.  Returns dict(final, dense, stiff, n_accept, n_reject, n_jump)."""
@@ -267,7 +288,9 @@ class Solver:
         final = out_final if out_final is not None else np.zeros((ns, n_eq))
         dense = None
         if want_dense and nq > 0:
-            dense = out_dense if out_dense is not None else np.zeros((ns, nq, n_eq))
+            ncol, dt = self.output_layout(uid)
+            dense = out_dense if out_dense is not None else np.zeros((ns, nq, ncol), dt)
+            assert dense.dtype == dt and dense.size == ns * nq * ncol and dense.flags.c_contiguous
         stiff = np.zeros(ns, np.int32)
         na, nr, nj = (np.zeros(ns, np.int64) for _ in range(3))
         _check(self._lib.hlm_run_rk45(self._h, uid, _p(y0), ns, t0, tf, _p(tq), nq, _p(final), _p(dense),
@@ -349,12 +372,12 @@ class Solver:
         return ptr.value, lo.value, hi.value
 
     def solve_fetch_window(self, host_dense: np.ndarray):
-        assert host_dense.dtype == np.float64 and host_dense.flags.c_contiguous
+        assert host_dense.dtype == self.output_layout(self._session[0])[1] and host_dense.flags.c_contiguous
         _check(self._lib.hlm_solve_fetch_window(self._h, _p(host_dense)))
 
     def solve_fetch_window_packed(self, host_win: np.ndarray) -> int:
-        """Last window packed as [ns][q_hi - q_lo][N_EQ]; returns the ticket for solve_wait_copy."""
-        assert host_win.dtype == np.float64 and host_win.flags.c_contiguous
+        """Last window packed as [ns][q_hi - q_lo][columns]; returns the ticket for solve_wait_copy."""
+        assert host_win.dtype == self.output_layout(self._session[0])[1] and host_win.flags.c_contiguous
         t = _I()
         _check(self._lib.hlm_solve_fetch_window_packed(self._h, _p(host_win), C.byref(t)))
         return t.value

@@ -109,6 +109,8 @@ struct hlm_ctx {
     long long max_attempts = 0;
     long long dense_window_bytes = 8LL << 30;
     int precision = 64;
+    unsigned int out_mask = 0;  // states a dense record carries (0 = all), hlm_set_output_states
+    int out_bits = 64;          // dense records as double or float, hlm_set_output_precision
 
     // per-link parameters (AoS copy kept on device so any model can be prepared lazily)
     DevBuf<unsigned char> sp_aos;
@@ -179,6 +181,18 @@ int use_device(hlm_ctx* c) {
     HLM_CUDA(cudaSetDevice(c->device));
     return 0;
 }
+
+// dense records: selected states of the session's model, columns per record, bytes per record
+unsigned int dense_mask(const hlm_ctx* c) {
+    const unsigned int all = (1u << c->n_eq) - 1u;
+    const unsigned int m = c->out_mask & all;
+    return m ? m : all;
+}
+int dense_ncol(const hlm_ctx* c) { return __builtin_popcount(dense_mask(c)); }
+size_t dense_elem(const hlm_ctx* c) { return c->out_bits == 32 ? sizeof(float) : sizeof(double); }
+size_t dense_record_bytes(const hlm_ctx* c) { return (size_t)dense_ncol(c) * dense_elem(c); }
+// DevBuf<double> elements that hold `bytes`
+size_t doubles_for(size_t bytes) { return (bytes + sizeof(double) - 1) / sizeof(double); }
 
 // ---- kernels that are not the hot path -----------------------------------------------------------
 
@@ -414,7 +428,7 @@ int dispatch_radau(hlm_ctx* c, const hlm::WindowArgs& a) {
 // =================================================================================================
 extern "C" {
 
-int hlm_abi_version(void) { return 3; }
+int hlm_abi_version(void) { return 4; }
 
 const char* hlm_last_error(void) { return g_err.c_str(); }
 
@@ -525,7 +539,9 @@ int hlm_upload_spatial_params(hlm_ctx* c, const void* aos, long long n, long lon
     const size_t rec = sizeof(hlm::SpatialParamsAoS);
     HLM_CUDA(c->sp_aos.reserve((size_t)std::max<long long>(n, 1) * rec));
     if (n > 0)
-        HLM_CUDA(cudaMemcpy2DAsync(c->sp_aos.p, rec, aos, (size_t)stride, rec, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        // cudaMemcpyDefault: `aos` may be host memory or — what the reference's run_rk45 is handed, a cudaMalloc'ed
+        // array (main.cpp:392-404) — device memory; unified addressing tells which
+        HLM_CUDA(cudaMemcpy2DAsync(c->sp_aos.p, rec, aos, (size_t)stride, rec, (size_t)n, cudaMemcpyDefault, c->stream));
     c->sp_n = n;
     c->sp_soa_uid = -1;  // columns are rebuilt on the next solve
     return HLM_OK;
@@ -608,6 +624,29 @@ int hlm_set_schedule(hlm_ctx* c, int mode) {
 int hlm_set_precision(hlm_ctx* c, int bits) {
     HLM_REQUIRE(c && (bits == 64 || bits == 32), "hlm_set_precision: bits must be 64 or 32");
     c->precision = bits;
+    return HLM_OK;
+}
+
+int hlm_set_output_states(hlm_ctx* c, unsigned int mask) {
+    HLM_REQUIRE(c, "hlm_set_output_states: ctx is NULL");
+    c->out_mask = mask;
+    return HLM_OK;
+}
+
+int hlm_set_output_precision(hlm_ctx* c, int bits) {
+    HLM_REQUIRE(c && (bits == 64 || bits == 32), "hlm_set_output_precision: bits must be 64 or 32");
+    c->out_bits = bits;
+    return HLM_OK;
+}
+
+int hlm_output_layout(hlm_ctx* c, int uid, int* n_columns, int* bytes_per_value) {
+    HLM_REQUIRE(c, "hlm_output_layout: ctx is NULL");
+    const ModelInfo* m = find_model(uid);
+    if (!m) return fail(HLM_ERR_INVALID, "hlm_output_layout: unknown model uid " + std::to_string(uid));
+    const unsigned int all = (1u << m->n_eq) - 1u;
+    const unsigned int eff = (c->out_mask & all) ? (c->out_mask & all) : all;
+    if (n_columns) *n_columns = __builtin_popcount(eff);
+    if (bytes_per_value) *bytes_per_value = c->out_bits == 32 ? 4 : 8;
     return HLM_OK;
 }
 
@@ -745,7 +784,7 @@ static int restart_impl(hlm_ctx* c, double t0, double tf, const double* tq, long
 
 // Queue the window kernel (and the implicit fallback, if on) for queries [q_lo, q_hi) over the links of tiles
 // [tile_lo, tile_lo + n_tiles); `dense` (may be NULL) receives the records, row 0 = link dense_sys0.
-static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, double* dense, long long tile_lo, long long n_tiles,
+static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, void* dense, long long tile_lo, long long n_tiles,
                         long long dense_sys0) {
     hlm::WindowArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -791,6 +830,9 @@ static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, double* dens
     a.q_lo = (int)q_lo;
     a.q_hi = (int)q_hi;
     a.dense = dense;
+    a.dense_mask = dense_mask(c);
+    a.dense_ncol = dense_ncol(c);
+    a.dense_f32 = c->out_bits == 32 ? 1 : 0;
     a.t0 = c->t0; a.tf = c->tf;
     a.prm = c->params[c->uid];
     a.ns = c->ns; a.ld = c->ld;
@@ -849,9 +891,8 @@ int hlm_solve_window(hlm_ctx* c, long long q_hi, int want_dense) {
             HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
             c->copy_pending[buf] = false;
         }
-        const size_t elems = (size_t)c->ns * (size_t)qw * (size_t)c->n_eq;
-        HLM_CUDA(c->dense[buf].reserve(elems));
-        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
+        // no memset: the window kernel writes every slot, zeros where a link never gets (rk45_window.cuh)
+        HLM_CUDA(c->dense[buf].reserve(doubles_for((size_t)c->ns * (size_t)qw * dense_record_bytes(c))));
         c->dense_cur = buf;
     }
     if (int r = queue_window(c, q_lo, q_hi, dense ? c->dense[buf].p : nullptr, 0, (c->ns + 31) / 32, 0)) return r;
@@ -872,17 +913,17 @@ int hlm_solve_window_buffer(hlm_ctx* c, void** dev_ptr, long long* q_lo, long lo
     return HLM_OK;
 }
 
-int hlm_solve_fetch_window(hlm_ctx* c, double* host_dense) {
+int hlm_solve_fetch_window(hlm_ctx* c, void* host_dense) {
     HLM_REQUIRE(c && host_dense, "hlm_solve_fetch_window: NULL argument");
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_fetch_window: no session");
     if (!c->win_has_dense) return HLM_OK;
     if (int r = use_device(c)) return r;
     const int buf = c->dense_cur;
     const long long qw = c->win_q_hi - c->win_q_lo;
-    const size_t row = (size_t)qw * c->n_eq * sizeof(double);         // one link's records of this window
-    const size_t host_pitch = (size_t)c->nq * c->n_eq * sizeof(double);  // one link's records of the run
+    const size_t row = (size_t)qw * dense_record_bytes(c);         // one link's records of this window
+    const size_t host_pitch = (size_t)c->nq * dense_record_bytes(c);  // one link's records of the run
     HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
-    double* dst = host_dense + (size_t)c->win_q_lo * c->n_eq;
+    char* dst = reinterpret_cast<char*>(host_dense) + (size_t)c->win_q_lo * dense_record_bytes(c);
     if (row == host_pitch)
         HLM_CUDA(cudaMemcpyAsync(dst, c->dense[buf].p, row * (size_t)c->ns, cudaMemcpyDeviceToHost, c->copy_stream));
     else
@@ -893,14 +934,14 @@ int hlm_solve_fetch_window(hlm_ctx* c, double* host_dense) {
     return HLM_OK;
 }
 
-int hlm_solve_fetch_window_packed(hlm_ctx* c, double* host_win, int* ticket) {
+int hlm_solve_fetch_window_packed(hlm_ctx* c, void* host_win, int* ticket) {
     HLM_REQUIRE(c && host_win, "hlm_solve_fetch_window_packed: NULL argument");
     if (!c->in_session) return fail(HLM_ERR_STATE, "hlm_solve_fetch_window_packed: no session");
     if (ticket) *ticket = c->dense_cur;
     if (!c->win_has_dense) return HLM_OK;
     if (int r = use_device(c)) return r;
     const int buf = c->dense_cur;
-    const size_t bytes = (size_t)c->ns * (size_t)(c->win_q_hi - c->win_q_lo) * c->n_eq * sizeof(double);
+    const size_t bytes = (size_t)c->ns * (size_t)(c->win_q_hi - c->win_q_lo) * dense_record_bytes(c);
     HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
     HLM_CUDA(cudaMemcpyAsync(host_win, c->dense[buf].p, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
     HLM_CUDA(cudaEventRecord(c->ev_copy_done[buf], c->copy_stream));
@@ -1016,11 +1057,11 @@ int hlm_solve_end(hlm_ctx* c, double* out_final, int* out_stiff, long long* out_
 // The state travels the same way: y0 of chunk i is uploaded (a third stream; PCIe is full duplex) and
 // initialised while earlier chunks integrate, and a chunk's final states, counters and codes are exported and
 // copied out right behind its dense records — so the call never waits for a whole-array transfer.
-static int run_link_chunks(hlm_ctx* c, const double* y0, double* out_dense, double* out_final, int* out_stiff,
+static int run_link_chunks(hlm_ctx* c, const double* y0, void* out_dense, double* out_final, int* out_stiff,
                            long long* out_acc, long long* out_rej, long long* out_jump) {
     const long long ns = c->ns, nq = c->nq;
     const int n_eq = c->n_eq;
-    const long long per_link = nq * n_eq * (long long)sizeof(double);
+    const long long per_link = nq * (long long)dense_record_bytes(c);
     const long long n_tiles_all = (ns + 31) / 32;
     const long long tiles_max = std::max<long long>(1, c->dense_window_bytes / (per_link * 32));
     const long long n_chunks = std::max<long long>((n_tiles_all + tiles_max - 1) / tiles_max, std::min<long long>(8, n_tiles_all));
@@ -1073,9 +1114,8 @@ static int run_link_chunks(hlm_ctx* c, const double* y0, double* out_dense, doub
             HLM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done[buf], 0));
             c->copy_pending[buf] = false;
         }
-        const size_t elems = (size_t)(hi - lo) * (size_t)nq * (size_t)n_eq;
-        HLM_CUDA(c->dense[buf].reserve(elems));
-        HLM_CUDA(cudaMemsetAsync(c->dense[buf].p, 0, elems * sizeof(double), c->stream));
+        const size_t chunk_bytes = (size_t)(hi - lo) * (size_t)per_link;
+        HLM_CUDA(c->dense[buf].reserve(doubles_for(chunk_bytes)));
         c->dense_cur = buf;
         HLM_CUDA(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
         if (int r = queue_window(c, 0, nq, c->dense[buf].p, tile, end - tile, lo)) return r;
@@ -1086,7 +1126,7 @@ static int run_link_chunks(hlm_ctx* c, const double* y0, double* out_dense, doub
         ++c->launches;
         HLM_CUDA(cudaEventRecord(c->ev_kernel_done[buf], c->stream));
         HLM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_kernel_done[buf], 0));
-        HLM_CUDA(cudaMemcpyAsync(out_dense + (size_t)lo * nq * n_eq, c->dense[buf].p, elems * sizeof(double),
+        HLM_CUDA(cudaMemcpyAsync(static_cast<char*>(out_dense) + (size_t)lo * (size_t)per_link, c->dense[buf].p, chunk_bytes,
                                  cudaMemcpyDeviceToHost, c->copy_stream));
         const size_t n = (size_t)(hi - lo);
         if (out_final)
@@ -1113,15 +1153,17 @@ static int run_link_chunks(hlm_ctx* c, const double* y0, double* out_dense, doub
 }
 
 int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0, double tf, const double* tq,
-                 long long nq, double* out_final, double* out_dense, int* out_stiff, long long* out_acc,
+                 long long nq, double* out_final, void* out_dense, int* out_stiff, long long* out_acc,
                  long long* out_rej, long long* out_jump) {
     HLM_REQUIRE(c, "hlm_run_rk45: ctx is NULL");
     if (!out_dense) nq = 0;  // nothing to emit: one window straight to tf
     // a large output leaves in chunks of links (run_link_chunks), which also pipelines the state in and out
     bool chunked = false;
     if (const ModelInfo* m = find_model(uid)) {
-        const long long per_q = ns * m->n_eq * (long long)sizeof(double);
-        const long long per_link = nq * m->n_eq * (long long)sizeof(double);
+        int ncol = m->n_eq, bytes = 8;
+        hlm_output_layout(c, uid, &ncol, &bytes);
+        const long long per_q = ns * ncol * (long long)bytes;
+        const long long per_link = nq * ncol * (long long)bytes;
         chunked = nq > 0 && ns > 0 && per_q * nq > std::min<long long>(256LL << 20, c->dense_window_bytes) &&
                   per_link * 32 <= c->dense_window_bytes;
     }
@@ -1132,7 +1174,7 @@ int hlm_run_rk45(hlm_ctx* c, int uid, const double* y0, long long ns, double t0,
     } else {
         // small output (one window), or a query list so long that even 32 links of it exceed a buffer:
         // windows over queries
-        const long long per_q = ns * c->n_eq * (long long)sizeof(double);
+        const long long per_q = ns * (long long)dense_record_bytes(c);
         const long long qw_max = std::max<long long>(1, c->dense_window_bytes / per_q);
         const long long n_win = (nq + qw_max - 1) / qw_max;
         const long long qw = (nq + n_win - 1) / n_win;  // even windows: the tail is not a sliver

@@ -96,7 +96,6 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
     const WindowArgs& a = ra.w;
     const unsigned int n_list = *ra.n_list;
     const bool run_to_end = (a.q_hi >= a.nq);
-    const int qw = a.q_hi - a.q_lo;
     const double rtol = a.prm.rtol, atol = a.prm.atol;
     for (unsigned int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_list; item += gridDim.x * blockDim.x) {
         const long long sys = ra.list[item];
@@ -231,13 +230,14 @@ template <class Model> __global__ void __launch_bounds__(64) radau_window_kernel
                     if (next_q >= a.q_hi) { overshoot = true; break; }
                     if (tq > t && a.dense != nullptr) {
                         const double th = (tq - t) / h;
-                        double* out = a.dense + ((sys - a.dense_sys0) * qw + (next_q - a.q_lo)) * N;
+                        long long out = dense_base(a, sys, next_q);
                         for (int i = 0; i < N; ++i) {
+                            if (!((a.dense_mask >> i) & 1u)) continue;
                             // collocation cubic through (0,0), (c1,Z1), (c2,Z2), (1,Z3): Newton form
                             const double d1 = Z[0][i] / C1, d2 = (Z[1][i] - Z[0][i]) / (C2 - C1), d3 = (Z[2][i] - Z[1][i]) / (1.0 - C2);
                             const double dd1 = (d2 - d1) / C2, dd2 = (d3 - d2) / (1.0 - C1);
                             const double ddd = dd2 - dd1;
-                            out[i] = y[i] + th * (d1 + (th - C1) * (dd1 + (th - C2) * ddd));
+                            dense_put(a, out++, y[i] + th * (d1 + (th - C1) * (dd1 + (th - C2) * ddd)));
                         }
                     }
                     ++next_q;
@@ -355,7 +355,6 @@ template <class Model> __global__ void __launch_bounds__(128) radau_warp_kernel(
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const unsigned int n_list = *ra.n_list;
     const bool run_to_end = (a.q_hi >= a.nq);
-    const int qw = a.q_hi - a.q_lo;
     const double rtol = a.prm.rtol, atol = a.prm.atol;
     // this lane's row of the 15 x 15 matrix is (stage rs, component ri); as a row of the 5 x 5 matrix, component lane
     const int rs = lane < N3 ? lane / N : 0, ri = lane < N3 ? lane % N : 0;
@@ -531,12 +530,13 @@ template <class Model> __global__ void __launch_bounds__(128) radau_warp_kernel(
                     if (next_q >= a.q_hi) { overshoot = true; break; }
                     if (tq > t && a.dense != nullptr && lane == 0) {
                         const double th = (tq - t) / h;
-                        double* out = a.dense + ((sys - a.dense_sys0) * qw + (next_q - a.q_lo)) * N;
+                        long long out = dense_base(a, sys, next_q);
                         for (int i = 0; i < N; ++i) {
+                            if (!((a.dense_mask >> i) & 1u)) continue;
                             const double d1 = Z[0][i] / C1, d2 = (Z[1][i] - Z[0][i]) / (C2 - C1), d3 = (Z[2][i] - Z[1][i]) / (1.0 - C2);
                             const double dd1 = (d2 - d1) / C2, dd2 = (d3 - d2) / (1.0 - C1);
                             const double ddd = dd2 - dd1;
-                            out[i] = y[i] + th * (d1 + (th - C1) * (dd1 + (th - C2) * ddd));
+                            dense_put(a, out++, y[i] + th * (d1 + (th - C1) * (dd1 + (th - C2) * ddd)));
                         }
                     }
                     ++next_q;

@@ -148,7 +148,10 @@ struct WindowArgs {
     const double* tq;      // [nq] ascending
     int nq;
     int q_lo, q_hi;        // this window's dense buffer covers queries [q_lo, q_hi)
-    double* dense;         // [ns][q_hi - q_lo][N_EQ] or nullptr
+    void* dense;           // [links of the launch][q_hi - q_lo][dense_ncol] of double (or float), or nullptr
+    unsigned int dense_mask;  // states a record carries, bit i = state i (hlm_set_output_states); dense_ncol = popcount
+    int dense_ncol;
+    int dense_f32;         // records stored as float (hlm_set_output_precision)
     double t0, tf;
     SolverParams prm;
     long long ns, ld;
@@ -191,10 +194,27 @@ __device__ __forceinline__ void route_publish(const WindowArgs& a, long long sys
     }
 }
 
-template <typename T, int N>
-struct StepOut {
-    T err;
-};
+// Dense records.  A record holds the selected states of one (link, query) in ascending state order; the window
+// kernels write EVERY slot of the launch's buffer exactly once — the interpolated states, or zeros for a query the
+// link never reaches (tq <= t0; queries after a stiff bail-out, a stall or tf) — so no memset precedes
+// a launch (it was 9.6 GB of extra HBM writes per step at 10 M links, serialised before the kernel).
+__device__ __forceinline__ long long dense_base(const WindowArgs& a, long long sys, int q) {
+    return ((sys - a.dense_sys0) * (long long)(a.q_hi - a.q_lo) + (q - a.q_lo)) * a.dense_ncol;
+}
+__device__ __forceinline__ void dense_put(const WindowArgs& a, long long idx, double v) {
+    if (a.dense_f32) static_cast<float*>(a.dense)[idx] = (float)v;
+    else static_cast<double*>(a.dense)[idx] = v;
+}
+// zero records for queries [q_from, q_to) of link sys (clipped to the window)
+static __device__ __noinline__ void dense_zero(const WindowArgs& a, long long sys, int q_from, int q_to) {
+    if (a.dense == nullptr) return;
+    if (q_from < a.q_lo) q_from = a.q_lo;
+    if (q_to > a.q_hi) q_to = a.q_hi;
+    for (int q = q_from; q < q_to; ++q) {
+        const long long b = dense_base(a, sys, q);
+        for (int c = 0; c < a.dense_ncol; ++c) dense_put(a, b + c, 0.0);
+    }
+}
 
 // One DOPRI5 attempt from (y, k0): fills k[1..6], y_next and the FSAL flag, returns err.
 // solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
@@ -294,7 +314,6 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
     const int lane = threadIdx.x & 31;
     const long long n_tiles = a.n_tiles;
     const bool run_to_end = (a.q_hi >= a.nq);
-    const int qw = a.q_hi - a.q_lo;
     const T rtol = (T)a.prm.rtol, atol = (T)a.prm.atol;
     const T safety = (T)a.prm.safety, minScale = (T)a.prm.minScale, maxScale = (T)a.prm.maxScale;
     const T h_floor = f::mul((T)a.prm.initialStep, (T)kMinStepFraction);     // rk45_kernel.cu:134
@@ -309,7 +328,10 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
         const long long sys = ((a.tile_lo + (long long)tile) << 5) + lane;
         if (sys >= a.ns) continue;
         int status = a.status[sys];
-        if (status != kActive) continue;
+        if (status != kActive) {  // finished, abandoned or in the fallback's hands: no record from this path
+            dense_zero(a, sys, a.q_lo, a.q_hi);
+            continue;
+        }
 
         // ---- load lane state (coalesced columns) ----
         T y[N], k[7][N], y_next[N];
@@ -341,6 +363,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
         // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
         // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
 
+        if (status != kActive) dense_zero(a, sys, next_q, a.q_hi);  // queries this link will never reach
         // ---- store lane state ----
 #pragma unroll
         for (int i = 0; i < N; ++i) a.y[(long long)i * a.ld + sys] = (double)y[i];
@@ -365,7 +388,6 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
 template <typename T> struct RunConsts {
     T rtol, atol, safety, minScale, maxScale, h_floor, h_stiff, tf;
     bool run_to_end;
-    int qw;
     __device__ __forceinline__ explicit RunConsts(const WindowArgs& a) {
         using f = fp<T>;
         rtol = (T)a.prm.rtol;
@@ -377,7 +399,6 @@ template <typename T> struct RunConsts {
         h_stiff = f::mul(f::sub((T)a.tf, (T)a.t0), (T)kMinStepFraction);  // rk45_kernel.cu:160
         tf = (T)a.tf;
         run_to_end = (a.q_hi >= a.nq);
-        qw = a.q_hi - a.q_lo;
     }
 };
 
@@ -435,7 +456,6 @@ template <class Model, typename T> struct LinkRun {
         const T rtol = c.rtol, atol = c.atol, safety = c.safety, minScale = c.minScale, maxScale = c.maxScale;
         const T h_floor = c.h_floor, h_stiff = c.h_stiff, tf = c.tf;
         const bool run_to_end = c.run_to_end;
-        const int qw = c.qw;
 #define HLM_LEAVE return true
 #define HLM_AGAIN return false
 #include "rk45_attempt_body.inc"
@@ -458,6 +478,7 @@ template <class Model, typename T> struct LinkRun {
     // A stiff bail-out at t >= tf cannot happen (the flag is only set with t < tf unchanged),
     // so kStiff here always means "flagged and unfinished" as rk45_kernel.cu:167-170.
     __device__ __forceinline__ void store(const WindowArgs& a) const {
+        if (status != kActive) dense_zero(a, sys, next_q, a.q_hi);  // queries this link will never reach
 #pragma unroll
         for (int i = 0; i < N; ++i) a.y[(long long)i * a.ld + sys] = (double)y[i];
         a.t[sys] = (double)t;
@@ -511,6 +532,8 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_lanes
                     r.status = kActive;
                     r.load(a, first + idx);
                     have = true;
+                } else {
+                    dense_zero(a, first + idx, a.q_lo, a.q_hi);
                 }
             }
         }

@@ -11,7 +11,7 @@
 //   time.origin: ISO8601       instant of t = 0 and of forcing sample 0 (default: time.start); a run
 //                              restarted from a final-state file keeps the origin and moves time.start
 //   forcings.dt_hours: {precipitation: 1, temperature: 24}   sample spacing when the files do not say
-//   output.dir / output.prefix / output.format (netcdf|csv) / output.dense (bool)
+//   output.dir / output.prefix / output.format (netcdf|csv) / output.dense (bool) / output.precision (64|32)
 //   solver.interval: "1d"      the run is driven in intervals of this length
 //   solver.max_attempts        per-link attempt budget per window (0 = unbounded like the reference)
 //   solver.stiff_fallback: true   links the RK45 path flags stiff are continued by the Radau IIA fallback
@@ -255,6 +255,7 @@ struct SimulationConfig {
         std::vector<int> states;
         std::string dir = ".", prefix = "", format = "netcdf";
         bool dense = true;
+        int precision = 64;  // dense records as double (the reference's type) or float
     } output;
     struct SolverInfo {
         std::string method = "RK45";
@@ -369,6 +370,10 @@ inline SimulationConfig config_from_yaml(const hlmyaml::Node& doc) {
     cfg.output.prefix = o["prefix"].as_string_or("");
     cfg.output.format = o["format"].as_string_or("netcdf");
     if (o["dense"]) cfg.output.dense = o["dense"].as_bool("output.dense");
+    if (o["precision"]) {
+        cfg.output.precision = (int)o["precision"].as_int("output.precision");
+        if (cfg.output.precision != 32 && cfg.output.precision != 64) throw std::runtime_error("config: output.precision must be 32 or 64");
+    }
     // 8) solver
     const Node& s = need(doc["solver"], "solver");
     cfg.solver.method = s["method"].as_string_or("RK45");

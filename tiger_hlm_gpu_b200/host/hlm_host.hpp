@@ -127,7 +127,8 @@ inline std::vector<int> forcingColumns(const std::vector<SpatialParams>& sp, con
 
 // ---- main.cpp:734-773 ----------------------------------------------------------------------------------
 /// final.csv: header "h_snow,var1,...", one row per system (default ostream precision, as the reference).
-inline void write_final_csv(const std::string& path, const std::vector<double>& y_final, int num_systems, int n_eq) {
+template <class Vec>  // std::vector<double> or rk45_api::FinalType
+inline void write_final_csv(const std::string& path, const Vec& y_final, int num_systems, int n_eq) {
     std::ofstream f(path);
     if (!f.is_open()) throw std::runtime_error("cannot open " + path);
     f << "h_snow";
@@ -143,7 +144,8 @@ inline void write_final_csv(const std::string& path, const std::vector<double>& 
 }
 
 /// dense.csv: header "time,var{i}_sys{s}...", time with setprecision(8) fixed, values setprecision(9).
-inline void write_dense_csv(const std::string& path, const std::vector<double>& dense, const std::vector<double>& tq,
+template <class Vec>  // std::vector<double> or rk45_api::DenseType
+inline void write_dense_csv(const std::string& path, const Vec& dense, const std::vector<double>& tq,
                             int num_systems, int n_eq) {
     std::ofstream f(path);
     if (!f.is_open()) throw std::runtime_error("cannot open " + path);

@@ -134,7 +134,7 @@ const char* hlmio_load_config_json(const char* path) {
               << ",\"output.print_minutes\":" << parse_interval_minutes(c.output.print_interval) << ",\"output.states\":[";
             for (size_t i = 0; i < c.output.states.size(); ++i) o << (i ? "," : "") << c.output.states[i];
             o << "],\"output.dir\":\"" << json_escape(c.output.dir) << "\",\"output.format\":\"" << json_escape(c.output.format) << "\""
-              << ",\"output.dense\":" << (c.output.dense ? "true" : "false") << ",\"solver.method\":\"" << json_escape(c.solver.method) << "\""
+              << ",\"output.dense\":" << (c.output.dense ? "true" : "false") << ",\"output.precision\":" << c.output.precision << ",\"solver.method\":\"" << json_escape(c.solver.method) << "\""
               << ",\"solver.override_tolerances\":" << (c.solver.override_tolerances ? "true" : "false") << ",\"solver.rtol\":" << c.solver.rtol
               << ",\"solver.atol\":" << c.solver.atol << ",\"solver.safety\":" << c.solver.safety << ",\"solver.min_scale\":" << c.solver.min_scale
               << ",\"solver.max_scale\":" << c.solver.max_scale << ",\"solver.override_initial_step\":" << (c.solver.override_initial_step ? "true" : "false")

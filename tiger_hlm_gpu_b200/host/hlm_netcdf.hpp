@@ -1166,17 +1166,21 @@ inline void write_final_netcdf(const std::string& filename, const double* h_y_fi
     }
 }
 
-/// outputs(system,time,variable) written window by window: the solver hands over [ns][qw][N_EQ] blocks
-/// of consecutive query ranges (hlm_solve_fetch_window) and only the selected states are kept
-/// (config.yaml output.states).  Rows are scattered into a shared mapping of the file, so a window
-/// costs one pass over its own bytes.
+/// outputs(system,time,variable) written window by window: the solver hands over blocks of consecutive query
+/// ranges (hlm_solve_fetch_window_packed) and only the selected states are kept (config.yaml output.states).
+/// Two source layouts: records of all n_eq states, of which the writer picks its own (the default), or — after
+/// set_packed_source() — records the DEVICE already cut down to the selected states in ascending state order
+/// (hlm_set_output_states), as double or float (hlm_set_output_precision; the file variable is then NC_FLOAT).
+/// Rows are scattered into a shared mapping of the file, so a window costs one pass over its own bytes.
 class DenseSeriesWriter {
   public:
     DenseSeriesWriter(const std::string& filename, const std::vector<double>& time_vals, const std::vector<int>& linkid_vals,
-                      const std::vector<int>& state_vals, int n_eq)
-        : w_(filename), nq_(time_vals.size()), ns_(linkid_vals.size()), n_eq_(n_eq), states_(state_vals) {
+                      const std::vector<int>& state_vals, int n_eq, bool store_float = false)
+        : w_(filename), nq_(time_vals.size()), ns_(linkid_vals.size()), n_eq_(n_eq), states_(state_vals), f32_(store_float) {
         for (int s : states_)
             if (s < 0 || s >= n_eq) throw std::runtime_error("output state index out of range");
+        src_cols_ = states_;
+        src_stride_ = (uint64_t)n_eq;
         const int ds = w_.def_dim("system", ns_), dt = w_.def_dim("time", nq_), dv = w_.def_dim("variable", states_.size());
         const int vs = w_.def_var("system", hlmnc::NC_INT, {ds});
         const int vt = w_.def_var("time", hlmnc::NC_DOUBLE, {dt});
@@ -1186,22 +1190,51 @@ class DenseSeriesWriter {
         w_.put_att_text(vt, "units", "minutes since start of simulation");
         w_.put_att_text(vv, "long_name", "state variable");
         w_.put_att_text(vv, "units", "various units");
-        vo_ = w_.def_var("outputs", hlmnc::NC_DOUBLE, {ds, dt, dv});
+        vo_ = w_.def_var("outputs", f32_ ? hlmnc::NC_FLOAT : hlmnc::NC_DOUBLE, {ds, dt, dv});
         w_.enddef();
         w_.put_var(vs, linkid_vals.data());
         w_.put_var(vt, time_vals.data());
         w_.put_var(vv, states_.data());
         out_ = w_.map_var(vo_);
     }
-    /// win = [ns][q_hi - q_lo][n_eq] (row pitch given in queries) holding queries [q_lo, q_hi)
-    void write_window(const double* win, uint64_t q_lo, uint64_t q_hi, uint64_t pitch_q) {
+    /// The source records hold only the distinct selected states, ascending (what the device writes under
+    /// hlm_set_output_states(output_mask())); values are float when the writer stores float.
+    void set_packed_source() {
+        std::vector<int> sorted = states_;
+        std::sort(sorted.begin(), sorted.end());
+        sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+        for (size_t v = 0; v < states_.size(); ++v)
+            src_cols_[v] = (int)(std::lower_bound(sorted.begin(), sorted.end(), states_[v]) - sorted.begin());
+        src_stride_ = sorted.size();
+        packed_ = true;
+    }
+    /// bit i set = state i is written: the argument of hlm_set_output_states
+    unsigned int output_mask() const {
+        unsigned int m = 0;
+        for (int s : states_) m |= 1u << s;
+        return m;
+    }
+    /// win = [ns][q_hi - q_lo][source record] (row pitch given in queries) holding queries [q_lo, q_hi);
+    /// values are double, or float for a packed float source
+    void write_window(const void* win, uint64_t q_lo, uint64_t q_hi, uint64_t pitch_q) {
         if (q_hi > nq_ || q_lo > q_hi) throw std::out_of_range("dense window outside the query range");
         const uint64_t nv = states_.size();
+        const bool src_f32 = packed_ && f32_;
+        const int es = f32_ ? 4 : 8;
         for (uint64_t s = 0; s < ns_; ++s)
             for (uint64_t q = q_lo; q < q_hi; ++q) {
-                const double* src = win + (s * pitch_q + (q - q_lo)) * n_eq_;
-                uint8_t* dst = out_ + ((s * nq_ + q) * nv) * 8;
-                for (uint64_t v = 0; v < nv; ++v) hlmnc::ClassicWriter::store_be(dst + 8 * v, src + states_[v], 8, 1);
+                const uint64_t rec = (s * pitch_q + (q - q_lo)) * src_stride_;
+                uint8_t* dst = out_ + ((s * nq_ + q) * nv) * es;
+                for (uint64_t v = 0; v < nv; ++v) {
+                    if (src_f32) {
+                        hlmnc::ClassicWriter::store_be(dst + 4 * v, static_cast<const float*>(win) + rec + src_cols_[v], 4, 1);
+                    } else if (f32_) {
+                        const float x = (float)static_cast<const double*>(win)[rec + src_cols_[v]];
+                        hlmnc::ClassicWriter::store_be(dst + 4 * v, &x, 4, 1);
+                    } else {
+                        hlmnc::ClassicWriter::store_be(dst + 8 * v, static_cast<const double*>(win) + rec + src_cols_[v], 8, 1);
+                    }
+                }
             }
     }
     void close() { w_.close(); }
@@ -1210,6 +1243,8 @@ class DenseSeriesWriter {
     hlmnc::ClassicWriter w_;
     uint64_t nq_, ns_;
     int n_eq_, vo_ = -1;
-    std::vector<int> states_;
+    std::vector<int> states_, src_cols_;
+    uint64_t src_stride_ = 0;
+    bool f32_ = false, packed_ = false;
     uint8_t* out_ = nullptr;
 };

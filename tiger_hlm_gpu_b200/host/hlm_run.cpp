@@ -282,12 +282,25 @@ int run(const Options& opt) {
     const bool csv = cfg.output.format == "csv";
     std::unique_ptr<DenseSeriesWriter> dense_writer;
     std::vector<double> dense_all;  // csv only
-    if (cfg.output.dense && !csv)
-        dense_writer.reset(new DenseSeriesWriter(out_dir + "/" + cfg.output.prefix + "dense" + suffix + ".nc", tq, linkids, states, n_eq));
+    // NetCDF output: output.states and output.precision are applied where the records are produced — the window
+    // kernel stores only the selected states (as float if asked), so only those bytes cross PCIe (the reference
+    // ships nothing selectively: main.cpp:788-793 writes every state).  The CSV writer keeps all states.
+    int rec_cols = n_eq;
+    size_t rec_elem = sizeof(double);
+    if (cfg.output.dense && !csv) {
+        const bool f32 = cfg.output.precision == 32;
+        dense_writer.reset(new DenseSeriesWriter(out_dir + "/" + cfg.output.prefix + "dense" + suffix + ".nc", tq, linkids, states, n_eq, f32));
+        dense_writer->set_packed_source();
+        check(hlm_set_output_states(ctx, dense_writer->output_mask()), "hlm_set_output_states");
+        check(hlm_set_output_precision(ctx, f32 ? 32 : 64), "hlm_set_output_precision");
+        int bytes = 8;
+        check(hlm_output_layout(ctx, cfg.model.uid, &rec_cols, &bytes), "hlm_output_layout");
+        rec_elem = (size_t)bytes;
+    }
     if (cfg.output.dense && csv) dense_all.assign((size_t)ns * tq.size() * n_eq, 0.0);
 
     // window size in queries: two pinned host buffers of at most 1 GiB each
-    const long long per_q = ns * n_eq * (long long)sizeof(double);
+    const long long per_q = ns * rec_cols * (long long)rec_elem;
     const long long qw_max = std::max<long long>(1, (1LL << 30) / per_q);
     Pinned pin[2];
     std::future<void> writing[2];
@@ -336,7 +349,7 @@ int run(const Options& opt) {
                 check(hlm_solve_window_buffer(ctx, nullptr, &wlo, &whi), "hlm_solve_window_buffer");
                 if (whi > wlo) {
                     if (writing[slot].valid()) writing[slot].get();  // the writer is done with this buffer
-                    pin[slot].reserve((size_t)ns * (size_t)(whi - wlo) * n_eq);
+                    pin[slot].reserve(((size_t)ns * (size_t)(whi - wlo) * rec_cols * rec_elem + 7) / 8);
                     int ticket = 0;
                     check(hlm_solve_fetch_window_packed(ctx, pin[slot].p, &ticket), "hlm_solve_fetch_window_packed");
                     const double* src = pin[slot].p;
