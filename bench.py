@@ -693,9 +693,10 @@ def main():
                 "roofline_frac": roofline_of(r32, uid, peak32, world)["frac"], "peak_tflops": peak32,
                 "link_status_after_run": r32["state"],
                 "note": "hlm_set_precision(32): FP32 state, stages and error control at the FP64 run's tolerances (rtol 1e-6 is ~8 "
-                        "float epsilons).  No reference counterpart (the reference is FP64 only); accuracy at exactly these settings "
-                        "is asserted in tests/test_gpu_parity.py::test_fp32_mode_at_the_bench_tolerances (within 50*(atol+rtol*|y|) "
-                        "+ 4 eps32*|y| of the FP64 run, every link finishing)"}
+                        "float epsilons).  No reference counterpart (the reference is FP64 only).  Accuracy at exactly these settings is "
+                        "asserted in tests/test_gpu_parity.py::test_fp32_mode_at_the_bench_tolerances: within 25*(atol+rtol*|y|) of FP64 "
+                        "under time-constant forcing; on this workload, whose states depend on the step sequence through the reference's "
+                        "step-start forcing sampling (SURVEY F7), within 8*(atol+rtol*|y|) + 2x FP64's own change under 10x tolerances"}
 
     # ---------------- wet arm: every link with surface storage, so Model204's pow() runs in every rhs ----------------
     wet = None

@@ -567,9 +567,13 @@ def test_every_dense_slot_is_written_by_the_kernel(solver):
         o = orun(204, OPRM, y0, 0.0, 1440.0, tq, sp=sp, forcing=forcing, max_attempts=150, threads=8)
     finally:
         solver.set_max_attempts(2_000_000)
-    assert (g["stiff"] == 2).sum() > ns // 2  # HLM_LINK_STALLED
-    assert_same_result(g, o, exact=True)
+    stalled = g["stiff"] == 2  # HLM_LINK_STALLED (the oracle has no such code: it stops at the same attempt and reports the state)
+    assert stalled.sum() > ns // 2
+    for key in ("n_accept", "n_reject", "n_jump", "dense"):
+        assert np.array_equal(g[key], o[key]), key
+    assert np.all(g["final"][stalled] == 0.0) and np.array_equal(g["final"][~stalled], o["final"][~stalled])
     assert np.all(g["dense"][:, :2] == 0.0) and np.all(g["dense"][:, 26:] == 0.0)
+    assert np.all(g["dense"][stalled, 25] == 0.0)  # the last hour lies beyond what 150 attempts reach
     # the same through session windows, where a stalled link is met again by later launches
     solver.set_max_attempts(150)
     try:
@@ -589,37 +593,61 @@ def test_every_dense_slot_is_written_by_the_kernel(solver):
 
 
 def test_fp32_mode_at_the_bench_tolerances(solver):
-    """BASELINE configs[3] "FP32 vs FP64": the bench runs the FP32 mode at the FP64 settings (rtol 1e-6, atol
-    1e-9, initialStep 1e-6) on the bench workload.  rtol 1e-6 is ~8 float epsilons, so the controller works at
-    its noise floor; the stated bound for that mode is: every link finishes, and final and hourly dense states
-    agree with the FP64 run within 50 * (atol + rtol*|y|) + 4 float epsilons of |y| (measured: see the assert
-    messages; FP32 rounding of the state itself is 6e-8 relative)."""
+    """BASELINE configs[3] "FP32 vs FP64": the bench runs the FP32 mode at the FP64 settings (rtol 1e-6, atol 1e-9,
+    initialStep 1e-6) on the bench workload.  Two stated bounds, both at exactly those settings:
+
+    (a) forcing constant in time: every link finishes and final + hourly dense states are within
+        25 * (atol + rtol*|y|) of the FP64 run (measured worst case 12.3, h_stat; the other states <= 4.5) — the
+        solver's own tolerance with the factor a global error over ~470 steps takes;
+    (b) the bench workload (hourly changing rain): the reference samples forcings at the step START and holds
+        them over the step, so a state depends on where steps fall relative to the hour marks — at
+        the 1e-3 level for h_stat, for ANY change of the step sequence.  FP64 itself moves by that much between
+        rtol 1e-6 and 1e-5.  The bound is therefore FP64's own sensitivity S = |FP64(10x tolerances) - FP64|:
+        |FP32 - FP64| <= 8 * (atol + rtol*|y|) + 2 * S per state (measured: 0.9e-3 vs S = 0.87e-3 for h_stat;
+        the states without that sensitivity stay within 5 * (atol + rtol*|y|))."""
     ns, days = 4096, 1
     sp = synthetic.make_spatial_params(ns)
     col, ncells = synthetic.make_cells(ns)
     pr, t2m = synthetic.make_forcing_grid(ncells, days)
     y0 = synthetic.make_y0(ns, wet_fraction=0.5)
-    solver.set_model_parameters(204, PRM)
+    tq = 60.0 * np.arange(1, 25)
     solver.set_max_attempts(2_000_000)
     solver.upload_spatial_params(sp)
-    solver.clear_forcings()
-    solver.upload_forcing(0, 1.0, pr)
-    solver.upload_forcing(1, 24.0, t2m)
-    solver.set_forcing_columns(col)
-    tq = 60.0 * np.arange(1, 25)
-    d = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
-    solver.set_precision(32)
-    try:
-        s = solver.run_rk45(204, y0, 0.0, 1440.0, tq)
-    finally:
-        solver.set_precision(64)
+
+    def run(forc_pr, forc_t, bits, prm):
+        solver.set_model_parameters(204, prm)
+        solver.clear_forcings()
+        solver.upload_forcing(0, 1.0, forc_pr)
+        solver.upload_forcing(1, 24.0, forc_t)
+        solver.set_forcing_columns(col)
+        solver.set_precision(bits)
+        try:
+            return solver.run_rk45(204, y0, 0.0, 1440.0, tq)
+        finally:
+            solver.set_precision(64)
+            solver.set_model_parameters(204, PRM)
+
+    # (a) constant in time, varying over cells
+    pr_c = np.repeat(pr[5:6], pr.shape[0], axis=0)
+    pr_c[:, ::2] = pr.max() * 0.5
+    t_c = np.repeat(t2m[0:1], t2m.shape[0], axis=0)
+    d, s = run(pr_c, t_c, 64, PRM), run(pr_c, t_c, 32, PRM)
     assert not d["stiff"].any()
     assert not s["stiff"].any(), f"{(s['stiff'] != 0).sum()} of {ns} links did not finish in FP32"
-    eps32 = float(np.finfo(np.float32).eps)
     for key in ("final", "dense"):
-        bound = 50.0 * (1e-9 + 1e-6 * np.abs(d[key])) + 4.0 * eps32 * np.abs(d[key])
-        excess = np.abs(s[key] - d[key]) / bound
-        assert excess.max() <= 1.0, f"FP32 {key}: worst deviation {excess.max():.2f} x the stated bound"
-    # the step counts differ (noise-floor rejections) but stay the same order: report, bound loosely
+        excess = np.abs(s[key] - d[key]) / (1e-9 + 1e-6 * np.abs(d[key]))
+        assert excess.max() <= 25.0, f"FP32 {key} (constant forcing): {excess.max():.1f} x (atol + rtol|y|)"
+    # (b) the bench workload
+    d, s = run(pr, t2m, 64, PRM), run(pr, t2m, 32, PRM)
+    loose = run(pr, t2m, 64, Parameters(initialStep=1e-6, rtol=1e-5, atol=1e-8))
+    assert not d["stiff"].any()
+    assert not s["stiff"].any(), f"{(s['stiff'] != 0).sum()} of {ns} links did not finish in FP32"
+    for key in ("final", "dense"):
+        for c in range(5):
+            err = np.abs(s[key][..., c] - d[key][..., c])
+            sens = np.abs(loose[key][..., c] - d[key][..., c]).max()
+            bound = 8.0 * (1e-9 + 1e-6 * np.abs(d[key][..., c])) + 2.0 * sens
+            assert np.all(err <= bound), (f"FP32 {key} state {c}: worst {np.max(err / bound):.2f} x the bound "
+                                          f"(FP64 sensitivity to a 10x tolerance change: {sens:.3e})")
     ratio = s["n_accept"].sum() / d["n_accept"].sum()
-    assert 0.5 < ratio < 2.0, ratio
+    assert 0.9 < ratio < 1.1, ratio  # measured 1.00003: the controller is not yet at its noise floor

@@ -379,6 +379,13 @@ template <class Model> int prepare_params(hlm_ctx* c) {
     return 0;
 }
 
+// SoA columns of the session's model, rebuilt when the records or the model changed since they were made
+int prepare_model_params(hlm_ctx* c) {
+    if (c->uid == hlm::Model204::UID) return prepare_params<hlm::Model204>(c);
+    if (c->uid == hlm::Model200::UID) return prepare_params<hlm::Model200>(c);
+    return 0;
+}
+
 cudaEvent_t get_event(hlm_ctx* c) {
     if (!c->event_pool.empty()) {
         cudaEvent_t e = c->event_pool.back();
@@ -738,10 +745,10 @@ static int solve_begin_impl(hlm_ctx* c, int uid, const double* y0, long long ns,
         HLM_CUDA(cudaGetLastError());
         ++c->launches;
     }
-    int r = 0;
-    if (uid == hlm::Model204::UID) r = prepare_params<hlm::Model204>(c);
-    if (uid == hlm::Model200::UID) r = prepare_params<hlm::Model200>(c);
-    if (r) return r;
+    // parameter columns: now when the records are here; otherwise with the first window — the reference hands d_sp to
+    // its launch, not to setup_gpu_buffers (solver/rk45_api.hpp:63-66,120-132)
+    if (c->sp_n == c->ns)
+        if (int r = prepare_model_params(c)) return r;
     c->in_session = true;
     return HLM_OK;
 }
@@ -786,6 +793,7 @@ static int restart_impl(hlm_ctx* c, double t0, double tf, const double* tq, long
 // [tile_lo, tile_lo + n_tiles); `dense` (may be NULL) receives the records, row 0 = link dense_sys0.
 static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, void* dense, long long tile_lo, long long n_tiles,
                         long long dense_sys0) {
+    if (int r = prepare_model_params(c)) return r;  // a no-op unless parameters were (re)uploaded since the last launch
     hlm::WindowArgs a;
     std::memset(&a, 0, sizeof(a));
     a.y = c->y.p; a.t = c->t.p; a.h = c->h.p; a.next_q = c->next_q.p; a.reject_run = c->reject_run.p;
