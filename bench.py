@@ -266,6 +266,66 @@ class Env:
             self.dist.destroy_process_group()
 
 
+def routed_partition_check(env, args):
+    """At N > 1, before anything is timed: a small routed network integrated by the N ranks with the exchange under
+    test, and by rank 0 alone; per-link final states and accepted-step counts must be the same bits (inflow sums run
+    in ascending original link index, so every partition gives the same arithmetic).  GPU against GPU: a property of
+    the path, not a comparison with the test-side restatement."""
+    import tiger_hlm_gpu_b200 as hlm
+    from tiger_hlm_gpu_b200 import routing, synthetic
+    torch, dist, world, rank = env.torch, env.dist, env.world, env.rank
+    ns, sub, dt, n_int = 40960, 512, args.couple_minutes, 12
+    sp = synthetic.apply_network(synthetic.make_spatial_params(ns, seed=5), synthetic.make_network(ns, subbasin_links=sub, seed=9))
+    col, ncells = synthetic.make_cells(ns, links_per_cell=97)
+    pr, t2m = synthetic.make_forcing_grid(ncells, 2, seed=31)
+    y0 = np.tile(np.array(synthetic.Y0_200), (ns, 1))
+    y0[:, 0] = np.random.default_rng(3).uniform(0.05, 5.0, ns)
+
+    def run(world_n, rank_n, dist_n):
+        plan = routing.plan(sp["stream"], sp["next_stream"], world_n, subbasin_links=sub)
+        topo = plan.ranks[rank_n]
+        sel = plan.order[topo.lo:topo.hi]
+        solver = hlm.Solver(env.local_rank)
+        solver.set_model_parameters(200, hlm.Parameters(*PRM6))
+        solver.set_max_attempts(5_000_000)
+        solver.upload_spatial_params(sp[sel])
+        solver.upload_forcing(0, 1.0, pr)
+        solver.upload_forcing(1, 24.0, t2m)
+        solver.set_forcing_columns(col[sel])
+        rs = routing.RoutedSolver(solver, 200, topo, world_n, plan.max_send, dist_n, exchange=args.exchange)
+        for i in range(n_int):
+            tq = np.array([dt * (i + 1)])
+            if i == 0:
+                rs.begin(y0[sel], 0.0, dt, tq)
+            rs.advance(dt * (i + 1), tq, want_dense=False)
+        r = rs.end()
+        n_ex = rs.exchanges
+        solver.close()
+        return sel, r, plan, n_ex
+
+    sel, r, plan, n_ex = run(world, rank, dist)
+    fin = torch.zeros(ns, 5, dtype=torch.float64, device=env.dev)
+    na = torch.zeros(ns, dtype=torch.float64, device=env.dev)
+    idx = torch.as_tensor(sel, device=env.dev)
+    fin[idx] = torch.as_tensor(r["final"], device=env.dev)
+    na[idx] = torch.as_tensor(r["n_accept"].astype(np.float64), device=env.dev)
+    dist.all_reduce(fin)  # every link is owned by exactly one rank: the sum is a gather
+    dist.all_reduce(na)
+    out = None
+    if rank == 0:
+        sel1, r1, _, _ = run(1, 0, None)
+        fin1 = np.zeros((ns, 5))
+        na1 = np.zeros(ns)
+        fin1[sel1] = r1["final"]
+        na1[sel1] = r1["n_accept"]
+        same = bool(np.array_equal(fin.cpu().numpy(), fin1) and np.array_equal(na.cpu().numpy(), na1))
+        out = {"bit_identical_to_one_rank": same, "links": ns, "intervals": n_int, "ranks": world, "exchanges": n_ex,
+               "cut_edges": plan.n_cut_edges, "halo_doubles": plan.halo_len, "accepted_steps": float(na1.sum()),
+               "what": "final states and accepted-step counts of every link: N ranks with the exchange under test vs rank 0 alone"}
+    dist.barrier()
+    return out
+
+
 def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
     """BASELINE configs[4]: Model 200 on a synthetic river network, partitioned by sub-basin over the ranks,
     boundary discharge exchanged once per coupling interval (NCCL all-gather, or peer-memory stores).  One step =
@@ -275,6 +335,7 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
     from tiger_hlm_gpu_b200 import routing, synthetic
 
     torch, dist, dev, world, rank = env.torch, env.dist, env.dev, env.world, env.rank
+    partition_check = routed_partition_check(env, args) if world > 1 else None
     ns_all = links_per_gpu * world
     dt = args.couple_minutes
     n_int = max(1, int(round(60.0 / dt)))
@@ -385,7 +446,7 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
                                   if world > 1 else "1 GPU, no exchange",
                    "l2": "inputs larger than L2 (state + parameters of the rank's links >> 126 MB)"},
         "accepted_steps_per_step": acc_all / K, "attempts_per_accepted": att_all / max(acc_all, 1.0),
-        "implicit_steps_total": radau_all, "exchanges_per_step": exchanges / K,
+        "implicit_steps_total": radau_all, "exchanges_per_step": exchanges / K, "partition_check": partition_check,
         "link_status_after_run": {k: state[k] for k in ("active", "done", "stiff", "stalled")},
         "e2e": e2e, "gpu_launches": int(launches_all),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp_peak, "unit": "TFLOP/s", "frac": achieved / fp_peak,
@@ -776,7 +837,7 @@ def main():
         try:
             rr = routed_record(env, args, Ks, W, 2_500_000, with_e2e=False)
             if rr is not None:
-                routed = {k: rr[k] for k in ("value", "unit", "ms_per_step", "steps", "exchanges_per_step", "accepted_steps_per_step",
+                routed = {k: rr[k] for k in ("value", "unit", "ms_per_step", "steps", "exchanges_per_step", "partition_check", "accepted_steps_per_step",
                                              "attempts_per_accepted", "implicit_steps_total", "link_status_after_run", "gpu_launches")}
                 routed["config"] = rr["config"]
                 routed["kernel_share_of_step"] = rr["roofline"]["kernel_share_of_step"]
