@@ -247,3 +247,38 @@ def test_driver_routed_model200(tmp_path):
     assert np.array_equal(den["outputs"], dense)
     q = r["final"][:, 0]
     assert q[-1] > 20 * q[0]                     # the chain outlet carries the discharge of everything above it
+
+
+def test_driver_routed_two_ranks_equal_one_rank(tmp_path):
+    """routing.enabled with WORLD_SIZE=2: two hlm_run processes, one per GPU, sub-basins dealt to the ranks, the boundary
+    links' discharge all-gathered over NCCL once per coupling interval (hlm_nccl.hpp).  Per link id the two ranks'
+    files must hold the bits of the single-rank run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one hlm_run process per GPU)")
+    write_case(tmp_path)
+    cfg = config_text("2021-01-01T00:00:00", "2021-01-01T06:00:00", states="[0, 1, 2, 3, 4]", prefix="r_")
+    cfg = cfg.replace("uid: 204", "uid: 200").replace("name: Model204", "name: Model200")
+    cfg += 'routing:\n  enabled: true\n  couple: "30m"\n  subbasin_links: 16\n'
+    (tmp_path / "routed.yaml").write_text(cfg)
+    run_driver(tmp_path, "routed.yaml")
+    one_f, one_d = read_nc(tmp_path / "out" / "r_final_rank_0.nc"), read_nc(tmp_path / "out" / "r_dense_rank_0.nc")
+    os.rename(tmp_path / "out", tmp_path / "out_one")
+    os.makedirs(tmp_path / "out")
+    env = dict(os.environ, WORLD_SIZE="2", HLM_RUN_TOKEN=f"t{os.getpid()}")
+    procs = [subprocess.Popen([RUN, str(tmp_path / "routed.yaml"), "--rank", str(r), "--world", "2", "--device", str(r)],
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "boundary links" in outs[0][0] and "cut edges" in outs[0][0]
+    ids, fin, den = [], [], []
+    for r in range(2):
+        f, d = read_nc(tmp_path / "out" / f"r_final_rank_{r}.nc"), read_nc(tmp_path / "out" / f"r_dense_rank_{r}.nc")
+        ids.append(f["system"]); fin.append(f["outputs"]); den.append(d["outputs"])
+    ids, fin, den = np.concatenate(ids), np.concatenate(fin), np.concatenate(den)
+    assert len(ids) == NS and len(set(ids.tolist())) == NS
+    order, order_one = np.argsort(ids), np.argsort(one_f["system"])
+    assert np.array_equal(fin[order], one_f["outputs"][order_one])
+    assert np.array_equal(den[order], one_d["outputs"][order_one])
+    assert not list((tmp_path / "out").glob("nccl_id*"))  # the id file is gone once the communicator exists

@@ -13,7 +13,9 @@
 //                                                     window integrates (two pinned buffers)
 //
 // One process per GPU.  Rank and world size come from --rank/--world or RANK/WORLD_SIZE/LOCAL_RANK
-// (torchrun / mpirun style launchers); ranks never talk to each other: links are independent.
+// (torchrun / mpirun style launchers).  Uncoupled models: ranks never talk to each other, links are independent.
+// Routed runs (routing.enabled): links are dealt to ranks by sub-basin and the ranks all-gather the boundary
+// links' discharge once per coupling interval over NCCL (hlm_nccl.hpp; the id file goes to output.dir).
 //
 // usage: hlm_run CONFIG.yaml [--rank R] [--world W] [--device D] [--root DIR] [--quiet]
 #include <dirent.h>
@@ -28,6 +30,9 @@
 #include "hlm_host.hpp"
 #include "hlm_routing.hpp"
 #include "hlm_netcdf.hpp"
+#ifdef HLM_HAVE_NCCL
+#include "hlm_nccl.hpp"  // routed runs over several ranks: the boundary all-gather
+#endif
 
 namespace {
 
@@ -184,13 +189,31 @@ int run(const Options& opt) {
     if (cfg.solver.method != "RK45") throw std::runtime_error("solver.method: only RK45 is available");
 
     // ---- per-link parameters: this rank's rows ----
+    // (routed runs: whole sub-basins in contiguous runs of the planned order, so that only sub-basin outlets that
+    // drain into another rank's sub-basin cross ranks; the plan is the same on every rank)
+    const bool routed = cfg.routing.enabled;
     std::vector<SpatialParams> sp;
+    hlm_b200::RoutePlan plan;
     if (n_sp > 0 || !cfg.local_params.file.empty()) {
         std::vector<SpatialParams> all = loadSpatialParams(join_path(root, cfg.local_params.file));
-        long long lo, hi;
-        shard_range((long long)all.size(), opt.world, opt.rank, lo, hi);
-        sp.assign(all.begin() + lo, all.begin() + hi);
-        say("links " + std::to_string(lo) + ".." + std::to_string(hi) + " of " + std::to_string(all.size()));
+        if (routed) {
+            std::vector<long long> stream(all.size()), next(all.size());
+            for (size_t s = 0; s < all.size(); ++s) {
+                stream[s] = all[s].stream;
+                next[s] = all[s].next_stream;
+            }
+            plan = hlm_b200::plan_routes(stream, next, opt.world, cfg.routing.subbasin_links);
+            const hlm_b200::RankTopology& tp = plan.ranks[(size_t)opt.rank];
+            sp.resize((size_t)tp.n_local());
+            for (long long k = 0; k < tp.n_local(); ++k) sp[(size_t)k] = all[(size_t)plan.order[(size_t)(tp.lo + k)]];
+            say("links: " + std::to_string(sp.size()) + " of " + std::to_string(all.size()) + " (" + std::to_string(plan.n_subbasins) +
+                " sub-basins over " + std::to_string(opt.world) + " rank(s), " + std::to_string(plan.n_cut_edges) + " cut edges)");
+        } else {
+            long long lo, hi;
+            shard_range((long long)all.size(), opt.world, opt.rank, lo, hi);
+            sp.assign(all.begin() + lo, all.begin() + hi);
+            say("links " + std::to_string(lo) + ".." + std::to_string(hi) + " of " + std::to_string(all.size()));
+        }
     }
     const long long ns = (long long)sp.size();
     if (ns == 0) { say("no links for this rank"); return 0; }
@@ -251,22 +274,27 @@ int run(const Options& opt) {
     std::vector<double> tq;
     for (double t = t_begin; t <= t_end; t += dq) tq.push_back(t);  // main.cpp:653-657
     // routed run: the interval is the coupling interval and every link continues across it (hlm_solve_advance)
-    const bool routed = cfg.routing.enabled;
+#ifdef HLM_HAVE_NCCL
+    std::unique_ptr<hlm_b200::NcclBoundaryExchange> exchange;
+#endif
+    const bool multi_rank_routed = routed && opt.world > 1;
     if (routed) {
-        if (opt.world != 1)
-            throw std::runtime_error("routing: this driver runs routed networks on one rank; a multi-rank run needs the host's "
-                                     "collective between intervals (hlm_b200::RoutedRun, INTEGRATION.md section 6)");
-        std::vector<long long> stream((size_t)ns), next((size_t)ns);
-        for (long long s = 0; s < ns; ++s) {
-            stream[(size_t)s] = sp[(size_t)s].stream;
-            next[(size_t)s] = sp[(size_t)s].next_stream;
-        }
-        const hlm_b200::RoutePlan plan = hlm_b200::plan_routes(stream, next, 1, cfg.routing.subbasin_links);
-        const hlm_b200::RankTopology& tp = plan.ranks[0];
-        check(hlm_route_set_topology(ctx, tp.up_ptr.data(), tp.up_idx.empty() ? nullptr : tp.up_idx.data(), ns, nullptr, 0),
+        const hlm_b200::RankTopology& tp = plan.ranks[(size_t)opt.rank];
+        check(hlm_route_set_topology(ctx, tp.up_ptr.data(), tp.up_idx.empty() ? nullptr : tp.up_idx.data(), ns,
+                                     tp.send_idx.empty() ? nullptr : tp.send_idx.data(), (long long)tp.send_idx.size()),
               "hlm_route_set_topology");
-        say("routing: " + std::to_string(tp.up_idx.size()) + " links drain into another link, " + std::to_string(plan.n_subbasins) +
-            " sub-basins, coupling interval " + cfg.routing.couple);
+        if (multi_rank_routed) {
+#ifdef HLM_HAVE_NCCL
+            exchange.reset(new hlm_b200::NcclBoundaryExchange(opt.world, opt.rank, device, join_path(root, cfg.output.dir), plan.max_send,
+                                                              plan.halo_len()));
+            check(hlm_set_stream(ctx, exchange->stream()), "hlm_set_stream");  // kernels and collectives on one stream
+            if (plan.max_send > 0) check(hlm_route_set_send_buffer(ctx, exchange->d_send()), "hlm_route_set_send_buffer");
+#else
+            throw std::runtime_error("routing with WORLD_SIZE > 1 needs the NCCL build of hlm_run (nccl.h was not found when it was built)");
+#endif
+        }
+        say("routing: " + std::to_string(tp.up_idx.size()) + " upstream entries, " + std::to_string(tp.send_idx.size()) +
+            " boundary links, coupling interval " + cfg.routing.couple);
     }
     check(hlm_set_stiff_fallback(ctx, (cfg.solver.stiff_fallback || routed) ? 1 : 0), "hlm_set_stiff_fallback");
     const double interval = parse_interval_minutes(routed ? cfg.routing.couple : cfg.solver.interval);
@@ -334,7 +362,17 @@ int run(const Options& opt) {
         const long long nq = (long long)(q_end - q_next);
         upload_forcing_for(ta, tb);
         if (first) check(hlm_solve_begin(ctx, cfg.model.uid, y0.data(), ns, ta, tb, tq.data() + q_next, nq), "hlm_solve_begin");
-        if (routed) check(hlm_route_gather(ctx, nullptr), "hlm_route_gather");  // inflow of this interval from the state at its start
+        if (routed) {  // inflow of this interval from the state at its start
+            double* halo = nullptr;
+#ifdef HLM_HAVE_NCCL
+            if (exchange && plan.max_send > 0) {
+                if (first) check(hlm_route_pack(ctx), "hlm_route_pack");  // afterwards the window kernel's epilogue has packed it
+                exchange->all_gather();
+                halo = exchange->d_halo();
+            }
+#endif
+            check(hlm_route_gather(ctx, halo), "hlm_route_gather");
+        }
         if (!first) {
             if (routed) check(hlm_solve_advance(ctx, tb, tq.data() + q_next, nq), "hlm_solve_advance");
             else check(hlm_solve_restart(ctx, ta, tb, tq.data() + q_next, nq), "hlm_solve_restart");

@@ -3,52 +3,22 @@
 // per coupling interval on the stream the library's kernels run on).  This is the host side INTEGRATION.md §6
 // describes; the reference's own multi-process plumbing is MPI (main.cpp:269-309), which this image lacks, so
 // ranks are plain processes launched with RANK / WORLD_SIZE / LOCAL_RANK in the environment (torchrun or a
-// shell loop) and the NCCL unique id travels through a file in OUTDIR.
+// shell loop) and the NCCL unique id travels through a file in OUTDIR (hlm_nccl.hpp).
 //
 // usage: RANK=r WORLD_SIZE=n LOCAL_RANK=r hlm_routed_nccl PARAMS.csv OUTDIR [hours=3] [couple_min=15] [subbasin_links=4096] [rain] [temp]
 // Writes OUTDIR/final_rank_<r>.csv: "stream,q,h_stat,h_surf,h_grav,h_aq" for the rank's links (17 significant digits).
-#include <cuda_runtime_api.h>
-#include <nccl.h>
-
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
-#include <thread>
 
 #include "hlm_host.hpp"
+#include "hlm_nccl.hpp"
 #include "hlm_routing.hpp"
 
 namespace {
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
-}
-void cuda_check(cudaError_t e, const char* what) {
-    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
-}
-void nccl_check(ncclResult_t r, const char* what) {
-    if (r != ncclSuccess) throw std::runtime_error(std::string(what) + ": " + ncclGetErrorString(r));
-}
-// rank 0 publishes the id under a temporary name and renames it; the others wait for the final name
-ncclUniqueId exchange_id(const std::string& path, int rank) {
-    ncclUniqueId id;
-    if (rank == 0) {
-        nccl_check(ncclGetUniqueId(&id), "ncclGetUniqueId");
-        const std::string tmp = path + ".tmp";
-        {
-            std::ofstream f(tmp, std::ios::binary);
-            f.write(reinterpret_cast<const char*>(&id), sizeof(id));
-        }
-        if (std::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot publish the NCCL id at " + path);
-        return id;
-    }
-    for (int tries = 0; tries < 1200; ++tries) {
-        std::ifstream f(path, std::ios::binary);
-        if (f.read(reinterpret_cast<char*>(&id), sizeof(id))) return id;
-        std::this_thread::sleep_for(std::chrono::milliseconds(50));
-    }
-    throw std::runtime_error("timed out waiting for the NCCL id at " + path);
 }
 }  // namespace
 
@@ -79,20 +49,9 @@ int main(int argc, char** argv) {
         std::vector<SpatialParams> sp((size_t)ns);
         for (long long k = 0; k < ns; ++k) sp[(size_t)k] = all[(size_t)plan.order[(size_t)(mine.lo + k)]];
 
-        cuda_check(cudaSetDevice(device), "cudaSetDevice");
-        cudaStream_t stream = nullptr;
-        cuda_check(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        ncclComm_t comm = nullptr;
-        double *d_send = nullptr, *d_halo = nullptr;
-        if (world > 1) {
-            const ncclUniqueId id = exchange_id(outdir + "/nccl_id.bin", rank);
-            nccl_check(ncclCommInitRank(&comm, world, id, rank), "ncclCommInitRank");
-            if (plan.max_send > 0) {
-                cuda_check(cudaMalloc(&d_send, sizeof(double) * (size_t)plan.max_send), "cudaMalloc");
-                cuda_check(cudaMalloc(&d_halo, sizeof(double) * (size_t)plan.halo_len()), "cudaMalloc");
-                cuda_check(cudaMemset(d_send, 0, sizeof(double) * (size_t)plan.max_send), "cudaMemset");
-            }
-        }
+        // stream, communicator (id through OUTDIR, hlm_nccl.hpp) and the two exchange buffers
+        hlm_b200::NcclBoundaryExchange ex(world, rank, device, outdir, plan.max_send, plan.halo_len());
+        cudaStream_t stream = ex.stream();
 
         hlm_b200::Context ctx(device);
         hlm_b200::check(hlm_set_stream(ctx.get(), stream), "hlm_set_stream");
@@ -110,16 +69,11 @@ int main(int argc, char** argv) {
         for (long long s = 0; s < ns; ++s)
             for (int i = 0; i < 5; ++i) y0[(size_t)s * 5 + i] = y0_common[i];
 
-        long long n_exchanges = 0;
         std::vector<double> fin((size_t)ns * 5);
         std::vector<int> code((size_t)ns);
         {
             hlm_b200::RoutedRun run(ctx, Model200::UID, mine, world, plan.max_send,
-                                    [&](const double* send, long long n, double* halo) {
-                                        nccl_check(ncclAllGather(send, halo, (size_t)n, ncclDouble, comm, stream), "ncclAllGather");
-                                        ++n_exchanges;
-                                    },
-                                    d_send, d_halo);
+                                    [&](const double*, long long, double*) { ex.all_gather(); }, ex.d_send(), ex.d_halo());
             const long long n_int = (long long)(hours * 60.0 / dt + 0.5);
             for (long long k = 0; k < n_int; ++k) {
                 const double tf = dt * (double)(k + 1);
@@ -139,11 +93,7 @@ int main(int argc, char** argv) {
             f << "\n";
         }
         std::printf("[rank %d/%d] %lld links, %zu boundary links, %lld all-gathers of %lld doubles, %lld links lost\n", rank, world, ns,
-                    mine.send_idx.size(), n_exchanges, plan.halo_len(), lost);
-        if (comm) ncclCommDestroy(comm);
-        if (d_send) cudaFree(d_send);
-        if (d_halo) cudaFree(d_halo);
-        cudaStreamDestroy(stream);
+                    mine.send_idx.size(), ex.exchanges(), plan.halo_len(), lost);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;
