@@ -107,9 +107,7 @@ def run_driver(d, cfg_name, world=1):
         assert "done:" in out.stdout
 
 
-def read_nc(path):
-    with netcdf_file(str(path), "r", mmap=False) as f:
-        return {k: np.array(v[:]) for k, v in f.variables.items()}
+from tests.ncread import is_hdf5, read_nc  # noqa: E402  (NetCDF-4 through the repo's reader, classic through SciPy)
 
 
 def expected(sp, col, pr, t2m, day_lo, day_hi, y0):
@@ -153,6 +151,8 @@ def test_driver_two_ranks_matches_python_api_and_oracle(tmp_path):
         lo, hi = shard_range(NS, 2, rank)
         fin = read_nc(tmp_path / "out" / f"final_rank_{rank}.nc")
         den = read_nc(tmp_path / "out" / f"dense_rank_{rank}.nc")
+        # the default container is the reference's: NetCDF-4 / HDF5, deflate + shuffle (I_O/output_series.cpp:31,56)
+        assert is_hdf5(tmp_path / "out" / f"final_rank_{rank}.nc") and is_hdf5(tmp_path / "out" / f"dense_rank_{rank}.nc")
         assert np.array_equal(fin["system"], sp_all["stream"][lo:hi])      # real link ids
         assert np.array_equal(den["variable"], [0, 2, 4])                  # output.states
         assert np.array_equal(den["time"], 60.0 * np.arange(DAYS * 24 + 1))
@@ -180,7 +180,9 @@ def test_driver_hot_start_continues_a_run(tmp_path):
     """Days 1-2, then day 3 restarted from the final-state file: same states as the uninterrupted run."""
     pr, t2m, col = write_case(tmp_path)
     (tmp_path / "full.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-04T00:00:00", states="[0, 1, 2, 3, 4]", prefix="full_"))
-    (tmp_path / "a.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-03T00:00:00", states="[0, 1, 2, 3, 4]", prefix="a_"))
+    # days 1-2 in the classic container (output.format: netcdf3), the rest in the default NetCDF-4: hot start reads either
+    (tmp_path / "a.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-03T00:00:00", states="[0, 1, 2, 3, 4]", prefix="a_")
+                                     .replace('  dir: "out"', '  dir: "out"\n  format: netcdf3'))
     (tmp_path / "b.yaml").write_text(config_text("2021-01-03T00:00:00", "2021-01-04T00:00:00", origin="2021-01-01T00:00:00", mode="hot",
                                                  init_file="out/a_final_rank_0.nc", states="[0, 1, 2, 3, 4]", prefix="b_"))
     for c in ("full.yaml", "a.yaml", "b.yaml"):
@@ -190,6 +192,7 @@ def test_driver_hot_start_continues_a_run(tmp_path):
     # links flagged stiff during days 1-2 have no final state (zero rows, solver/rk45_kernel.cu:167-170):
     # the uninterrupted run keeps them flagged, a restart would start them from zeros
     a_f = read_nc(tmp_path / "out" / "a_final_rank_0.nc")
+    assert not is_hdf5(tmp_path / "out" / "a_final_rank_0.nc") and is_hdf5(tmp_path / "out" / "b_final_rank_0.nc")
     ok = a_f["outputs"].any(axis=1)
     assert 50 < ok.sum() < NS
     assert np.array_equal(b_f["system"], full_f["system"])

@@ -43,6 +43,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+NC4, CLASSIC = 0, 1  # the `format` argument of the hlmio_write_* entry points
+
+
 def read_var(io, path, name, start=None, count=None):
     shape = (C.c_longlong * 8)()
     es = C.c_int()
@@ -69,8 +72,8 @@ def test_write_dense_and_final_netcdf_read_back_by_scipy(io, tmp_path):
     ids = (420000000 + np.arange(ns)).astype(np.int32)
     states = np.arange(n, dtype=np.int32)
     pd, pf = str(tmp_path / "dense.nc"), str(tmp_path / "final.nc")
-    io.hlmio_write_dense_netcdf(pd.encode(), _p(dense), _p(t), _p(ids), _p(states), nq, ns, n)
-    io.hlmio_write_final_netcdf(pf.encode(), _p(final), _p(ids), _p(states), ns, n)
+    io.hlmio_write_dense_netcdf(pd.encode(), _p(dense), _p(t), _p(ids), _p(states), nq, ns, n, CLASSIC, 0)
+    io.hlmio_write_final_netcdf(pf.encode(), _p(final), _p(ids), _p(states), ns, n, CLASSIC, 0)
     with netcdf_file(pd, "r", mmap=False) as f:
         assert f.version_byte == 2
         assert {k: v for k, v in f.dimensions.items()} == {"system": ns, "time": nq, "variable": n}
@@ -103,7 +106,7 @@ def test_windowed_writer_equals_whole_array_writer(io, tmp_path, qw):
     ids = np.arange(100, 100 + ns, dtype=np.int32)
     states = np.array([4, 0, 2], np.int32)  # output.states subset, in the caller's order
     p = str(tmp_path / f"win{qw}.nc")
-    rc = io.hlmio_write_dense_windows(p.encode(), _p(dense), _p(t), _p(ids), _p(states), len(states), nq, ns, n, qw)
+    rc = io.hlmio_write_dense_windows(p.encode(), _p(dense), _p(t), _p(ids), _p(states), len(states), nq, ns, n, qw, CLASSIC, 0, 0, 0)
     assert rc == 0, io.hlmio_last_error().decode()
     with netcdf_file(p, "r", mmap=False) as f:
         assert f.variables["outputs"].shape == (ns, nq, 3)
@@ -117,7 +120,7 @@ def test_windowed_writer_rejects_bad_state(io, tmp_path):
     t = np.arange(2.0)
     ids = np.arange(2, dtype=np.int32)
     states = np.array([5], np.int32)
-    rc = io.hlmio_write_dense_windows(str(tmp_path / "x.nc").encode(), _p(d), _p(t), _p(ids), _p(states), 1, 2, 2, 5, 1)
+    rc = io.hlmio_write_dense_windows(str(tmp_path / "x.nc").encode(), _p(d), _p(t), _p(ids), _p(states), 1, 2, 2, 5, 1, NC4, 4, 0, 0)
     assert rc != 0 and b"state index" in io.hlmio_last_error()
 
 
@@ -202,6 +205,167 @@ def test_hdf5_reader_decodes_the_reference_outputs(io):
     assert np.array_equal(read_var(io, pd, "system"), np.arange(10.0))  # the reference writes 0..ns-1 (main.cpp:788-793)
     # hyperslabs cut through the single compressed chunk
     assert np.array_equal(read_var(io, pd, "outputs", start=[3, 100, 1], count=[2, 50, 3]), dense[3:5, 100:150, 1:4])
+
+
+# ---------------------------------------------------------------------------------- NetCDF-4 / HDF5 writer
+class H5:
+    """A minimal walk over an HDF5 file of the kind netcdf-c writes (superblock v2, version-2 object headers, compact
+    links): just enough to lay the reference's own files and this repo's side by side, message by message."""
+    NAMES = {1: "dataspace", 2: "linkinfo", 3: "datatype", 5: "fill", 6: "link", 8: "layout", 0xa: "groupinfo", 0xb: "filter",
+             0xc: "attr", 0x10: "cont", 0x15: "attrinfo", 0: "nil"}
+
+    def __init__(self, path):
+        self.b = open(path, "rb").read()
+        b = self.b
+        assert b[:8] == b"\x89HDF\r\n\x1a\n"
+        self.superblock_version, self.size_of_offsets, self.size_of_lengths = b[8], b[9], b[10]
+        self.base, self.ext, self.eof, self.root = np.frombuffer(b[12:44], "<u8").tolist()
+        self.superblock_checksum = int.from_bytes(b[44:48], "little")
+        self.objects = {}
+        for t, body in self.messages(self.root):
+            if t == 6:
+                fl, q = body[1], 2
+                q += (1 if fl & 8 else 0) + (8 if fl & 4 else 0) + (1 if fl & 0x10 else 0)
+                ls = 1 << (fl & 3)
+                ln = int.from_bytes(body[q:q + ls], "little")
+                q += ls
+                self.objects[body[q:q + ln].decode()] = int.from_bytes(body[q + ln:q + ln + 8], "little")
+
+    def chunks_of(self, addr):
+        """(start, end) of every header chunk of the object at addr, checksum excluded: [(lo, hi, stored_checksum)]"""
+        b = self.b
+        assert b[addr:addr + 4] == b"OHDR" and b[addr + 4] == 2
+        fl = b[addr + 5]
+        p = addr + 6 + (16 if fl & 0x20 else 0) + (4 if fl & 0x10 else 0)
+        n = 1 << (fl & 3)
+        size0 = int.from_bytes(b[p:p + n], "little")
+        p += n
+        return fl, p, size0
+
+    def messages(self, addr):
+        b = self.b
+        fl, p, size0 = self.chunks_of(addr)
+        blocks, out = [(p, p + size0)], []
+        self.checks = getattr(self, "checks", [])
+        self.checks.append((addr, p + size0))
+        while blocks:
+            p, end = blocks.pop(0)
+            while p + 4 <= end:
+                t, sz = b[p], int.from_bytes(b[p + 1:p + 3], "little")
+                hp = p + 4 + (2 if fl & 4 else 0)
+                body = b[hp:hp + sz]
+                out.append((t, body))
+                if t == 0x10:
+                    ca, cl = int.from_bytes(body[:8], "little"), int.from_bytes(body[8:16], "little")
+                    assert b[ca:ca + 4] == b"OCHK"
+                    blocks.append((ca + 4, ca + cl - 4))
+                    self.checks.append((ca, ca + cl - 4))
+                p = hp + sz
+        return out
+
+    def by_type(self, name):
+        msgs = self.messages(self.objects[name])
+        return {self.NAMES.get(t, hex(t)): body for t, body in msgs if t not in (0, 0xc, 0x10)}
+
+    def attr_names(self, name):
+        out = []
+        for t, body in self.messages(self.objects[name]):
+            if t == 0xc:
+                n = int.from_bytes(body[2:4], "little")
+                out.append(body[9:9 + n - 1].decode())
+        return out
+
+
+def test_lookup3_matches_the_checksums_in_the_reference_files(io):
+    """HDF5's metadata checksum (Jenkins lookup3), as implemented for the writer, against the checksums netcdf-c/HDF5
+    stored in the reference's own outputs: the superblock's and every object-header chunk's."""
+    io.hlmio_lookup3.restype = C.c_uint
+    io.hlmio_lookup3.argtypes = [C.c_char_p, C.c_longlong]
+    for f in ("final_example.nc", "dense_example.nc"):
+        h = H5(os.path.join(GOLD, f))
+        assert io.hlmio_lookup3(h.b[:44], 44) == h.superblock_checksum
+        for name in h.objects:
+            h.messages(h.objects[name])
+        assert len(h.checks) >= 6
+        for lo, hi in h.checks:
+            assert io.hlmio_lookup3(h.b[lo:hi], hi - lo) == int.from_bytes(h.b[hi:hi + 4], "little"), (f, lo)
+
+
+def test_netcdf4_writer_lays_the_file_out_like_the_reference(io, tmp_path):
+    """The reference's outputs are NetCDF-4 with shuffle + deflate on `outputs` (I_O/output_series.cpp:31,56,88,109).  The
+    values of src/final_example.nc and src/dense_example.nc written by this repo's NetCDF-4 writer give files with the same
+    superblock version, the same dataspace / datatype / fill / filter-pipeline messages byte for byte, the same layout class,
+    version and chunk shape (one chunk), the same attribute names in the same order; they decode to the same values through
+    the reader that decodes the reference's, and every checksum in them verifies."""
+    io.hlmio_lookup3.restype = C.c_uint
+    io.hlmio_lookup3.argtypes = [C.c_char_p, C.c_longlong]
+    g = np.load(os.path.join(GOLD, "model204_example.npz"))
+    final = np.ascontiguousarray(g["final"])
+    dense = np.ascontiguousarray(np.repeat(g["dense_sys0"][None], 10, axis=0))
+    ids, states, t = np.arange(10, dtype=np.int32), np.arange(5, dtype=np.int32), np.arange(2881.0)
+    pf, pd = str(tmp_path / "final.nc"), str(tmp_path / "dense.nc")
+    io.hlmio_write_final_netcdf(pf.encode(), _p(final), _p(ids), _p(states), 10, 5, NC4, 4)
+    io.hlmio_write_dense_netcdf(pd.encode(), _p(dense), _p(t), _p(ids), _p(states), 2881, 10, 5, NC4, 4)
+    for mine, ref in ((pf, "final_example.nc"), (pd, "dense_example.nc")):
+        a, r = H5(mine), H5(os.path.join(GOLD, ref))
+        assert (a.superblock_version, a.size_of_offsets, a.size_of_lengths) == (r.superblock_version, r.size_of_offsets, r.size_of_lengths) == (2, 8, 8)
+        assert a.eof == len(a.b) and a.base == 0
+        assert list(a.objects) == list(r.objects) or sorted(a.objects) == sorted(r.objects)
+        for name in r.objects:
+            ma, mr = a.by_type(name), r.by_type(name)
+            for kind in ("dataspace", "datatype", "fill", "filter"):
+                assert ma.get(kind) == mr.get(kind), (ref, name, kind)
+            la, lr = ma["layout"], mr["layout"]
+            assert la[:2] == lr[:2]                      # version 3, class (1 contiguous / 2 chunked)
+            if la[1] == 2:
+                assert la[2] == lr[2] and la[11:] == lr[11:]  # dimensionality, chunk shape + element size (the B-tree address differs)
+            else:
+                assert la[10:] == lr[10:]                # size in bytes
+            assert a.attr_names(name) == r.attr_names(name), (ref, name)
+        a.checks = []
+        for name in a.objects:
+            a.messages(a.objects[name])
+        a.messages(a.root)
+        for lo, hi in a.checks:
+            assert io.hlmio_lookup3(a.b[lo:hi], hi - lo) == int.from_bytes(a.b[hi:hi + 4], "little")
+        assert io.hlmio_lookup3(a.b[:44], 44) == a.superblock_checksum
+    assert np.array_equal(read_var(io, pf, "outputs"), final)
+    assert np.array_equal(read_var(io, pd, "outputs"), dense)
+    assert np.array_equal(read_var(io, pd, "time"), t) and np.array_equal(read_var(io, pd, "system"), ids)
+    assert os.path.getsize(pd) < dense.nbytes // 4  # deflate + shuffle did their work (the reference's file: 114 009 bytes)
+    # level 0: no filter, contiguous (output_series.cpp:56 only deflates when the level is positive)
+    p0 = str(tmp_path / "final0.nc")
+    io.hlmio_write_final_netcdf(p0.encode(), _p(final), _p(ids), _p(states), 10, 5, NC4, 0)
+    m0 = H5(p0).by_type("outputs")
+    assert "filter" not in m0 and m0["layout"][1] == 1 and np.array_equal(read_var(io, p0, "outputs"), final)
+
+
+@pytest.mark.parametrize("ns,nq,qw,staging,f32", [(33, 11, 4, 0, 0), (33, 11, 1, 2000, 0), (700, 40, 7, 9000, 0), (700, 40, 40, 0, 1),
+                                                   (5, 300, 13, 600, 1), (3000, 130, 50, 100000, 0)])
+def test_netcdf4_windowed_writer_many_chunks(io, tmp_path, ns, nq, qw, staging, f32):
+    """DenseSeriesWriter's NetCDF-4 container: windows of any length into chunk-rows of queries (a small staging slab forces
+    many rows, partial last rows and system chunks that overhang), a multi-level chunk B-tree, float or double values,
+    output.states in the caller's order; read back whole and by hyperslab through the HDF5 reader."""
+    rng = np.random.default_rng(ns + nq)
+    n = 5
+    dense = rng.standard_normal((ns, nq, n))
+    t = 15.0 * np.arange(nq)
+    ids = np.arange(100, 100 + ns, dtype=np.int32)
+    states = np.array([4, 0, 2], np.int32)
+    p = str(tmp_path / "win.nc")
+    rc = io.hlmio_write_dense_windows(p.encode(), _p(dense), _p(t), _p(ids), _p(states), len(states), nq, ns, n, qw, NC4, 4, f32, staging)
+    assert rc == 0, io.hlmio_last_error().decode()
+    want = dense[:, :, states]
+    if f32:
+        want = want.astype(np.float32).astype(np.float64)
+    got = read_var(io, p, "outputs")
+    assert got.shape == (ns, nq, 3) and np.array_equal(got, want)
+    assert np.array_equal(read_var(io, p, "variable"), states) and np.array_equal(read_var(io, p, "time"), t)
+    s0, q0 = ns // 3, nq // 4
+    assert np.array_equal(read_var(io, p, "outputs", start=[s0, q0, 1], count=[ns - s0, nq - q0, 2]), want[s0:, q0:, 1:])
+    h = H5(p)
+    lay = h.by_type("outputs")["layout"]
+    assert lay[1] == 2 and h.by_type("outputs")["datatype"][4] == (4 if f32 else 8)
 
 
 # ---------------------------------------------------------------------------------- config.yaml

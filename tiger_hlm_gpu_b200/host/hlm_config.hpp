@@ -11,7 +11,8 @@
 //   time.origin: ISO8601       instant of t = 0 and of forcing sample 0 (default: time.start); a run
 //                              restarted from a final-state file keeps the origin and moves time.start
 //   forcings.dt_hours: {precipitation: 1, temperature: 24}   sample spacing when the files do not say
-//   output.dir / output.prefix / output.format (netcdf|csv) / output.dense (bool) / output.precision (64|32)
+//   output.dir / output.prefix / output.format (netcdf = NetCDF-4 as the reference writes | netcdf3 | csv) /
+//   output.compression_level (0-9, default 4: output_series.hpp) / output.dense (bool) / output.precision (64|32)
 //   solver.interval: "1d"      the run is driven in intervals of this length
 //   solver.max_attempts        per-link attempt budget per window (0 = unbounded like the reference)
 //   solver.stiff_fallback: true   links the RK45 path flags stiff are continued by the Radau IIA fallback
@@ -256,6 +257,7 @@ struct SimulationConfig {
         std::string dir = ".", prefix = "", format = "netcdf";
         bool dense = true;
         int precision = 64;  // dense records as double (the reference's type) or float
+        int compression_level = 4;  // deflate level of `outputs` in NetCDF-4 files (output_series.hpp:24,44), 0 = none
     } output;
     struct SolverInfo {
         std::string method = "RK45";
@@ -369,6 +371,14 @@ inline SimulationConfig config_from_yaml(const hlmyaml::Node& doc) {
     cfg.output.dir = o["dir"].as_string_or(".");
     cfg.output.prefix = o["prefix"].as_string_or("");
     cfg.output.format = o["format"].as_string_or("netcdf");
+    if (cfg.output.format == "netcdf4") cfg.output.format = "netcdf";
+    if (cfg.output.format == "classic") cfg.output.format = "netcdf3";
+    if (cfg.output.format != "netcdf" && cfg.output.format != "netcdf3" && cfg.output.format != "csv")
+        throw std::runtime_error("config: output.format must be netcdf, netcdf3 or csv");
+    if (o["compression_level"]) {
+        cfg.output.compression_level = (int)o["compression_level"].as_int("output.compression_level");
+        if (cfg.output.compression_level < 0 || cfg.output.compression_level > 9) throw std::runtime_error("config: output.compression_level must be 0..9");
+    }
     if (o["dense"]) cfg.output.dense = o["dense"].as_bool("output.dense");
     if (o["precision"]) {
         cfg.output.precision = (int)o["precision"].as_int("output.precision");

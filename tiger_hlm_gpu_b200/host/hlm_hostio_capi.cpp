@@ -93,17 +93,22 @@ int hlmio_load_time_chunk(const char* path, const char* var, long long start, lo
         }
     });
 }
-void hlmio_write_dense_netcdf(const char* path, const double* dense, const double* t, const int* ids, const int* states, int nq, int ns, int n_eq) {
-    write_dense_netcdf(path, dense, t, ids, states, nq, ns, n_eq, 0);
+/// format: 0 = NetCDF-4 (the reference's container), 1 = classic; level = deflate level of `outputs` (NetCDF-4)
+void hlmio_write_dense_netcdf(const char* path, const double* dense, const double* t, const int* ids, const int* states, int nq, int ns, int n_eq,
+                              int format, int level) {
+    write_dense_netcdf(path, dense, t, ids, states, nq, ns, n_eq, level, format == 1 ? NcFormat::kClassic : NcFormat::kNetcdf4);
 }
-void hlmio_write_final_netcdf(const char* path, const double* fin, const int* ids, const int* states, int ns, int n_eq) {
-    write_final_netcdf(path, fin, ids, states, ns, n_eq, 0);
+void hlmio_write_final_netcdf(const char* path, const double* fin, const int* ids, const int* states, int ns, int n_eq, int format, int level) {
+    write_final_netcdf(path, fin, ids, states, ns, n_eq, level, format == 1 ? NcFormat::kClassic : NcFormat::kNetcdf4);
 }
-/// the windowed writer: `n_win` windows of `qw` queries each taken from the full array [ns][nq][n_eq]
+/// the windowed writer: windows of `qw` queries each taken from the full array [ns][nq][n_eq]; store_float: the file
+/// variable is NC_FLOAT; staging_bytes bounds the NetCDF-4 writer's slab (small values force many chunk-rows)
 int hlmio_write_dense_windows(const char* path, const double* dense, const double* t, const int* ids, const int* states, int n_states,
-                              int nq, int ns, int n_eq, int qw) {
+                              int nq, int ns, int n_eq, int qw, int format, int level, int store_float, long long staging_bytes) {
     return guarded([&] {
-        DenseSeriesWriter w(path, std::vector<double>(t, t + nq), std::vector<int>(ids, ids + ns), std::vector<int>(states, states + n_states), n_eq);
+        DenseSeriesWriter w(path, std::vector<double>(t, t + nq), std::vector<int>(ids, ids + ns), std::vector<int>(states, states + n_states), n_eq,
+                            store_float != 0, format == 1 ? NcFormat::kClassic : NcFormat::kNetcdf4, level,
+                            staging_bytes > 0 ? (uint64_t)staging_bytes : (256ULL << 20));
         std::vector<double> win;
         for (int q0 = 0; q0 < nq; q0 += qw) {
             const int q1 = std::min(nq, q0 + qw);
@@ -115,6 +120,8 @@ int hlmio_write_dense_windows(const char* path, const double* dense, const doubl
         w.close();
     });
 }
+/// HDF5's metadata checksum (lookup3), so a test can check it against the checksums in the reference's own files
+unsigned int hlmio_lookup3(const unsigned char* p, long long n) { return hlmnc::lookup3(p, (size_t)n); }
 /// load_config -> a flat JSON object of everything SimulationConfig holds
 const char* hlmio_load_config_json(const char* path) {
     g_text.clear();

@@ -39,6 +39,8 @@
 
 static_assert(__BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__, "host byte order assumed little-endian");
 
+#include "hlm_netcdf4_writer.hpp"
+
 namespace hlmnc {
 
 enum NcType : int {
@@ -1113,30 +1115,60 @@ class NetCDFLoader {
     std::string fileName, varName;
 };
 
+/// Container of an output file: NetCDF-4 (HDF5; what the reference writes, I_O/output_series.cpp:31,88) or the
+/// classic 64-bit-offset format (no compression; every NetCDF reader, SciPy's included, opens it).
+enum class NcFormat { kNetcdf4, kClassic };
+
+namespace hlmnc_detail {
+// the reference's dimensions, coordinate variables and attributes (output_series.cpp:31-52,88-105), on either writer
+template <class W> struct SeriesVars { int vs, vt, vv, vo; };
+template <class W>
+SeriesVars<W> define_series(W& w, uint64_t ns, uint64_t nq, uint64_t nv, bool with_time, int out_type) {
+    SeriesVars<W> r{};
+    const int ds = w.def_dim("system", ns);
+    const int dt = with_time ? w.def_dim("time", nq) : -1;
+    const int dv = w.def_dim("variable", nv);
+    r.vs = w.def_var("system", hlmnc::NC_INT, {ds});
+    r.vt = with_time ? w.def_var("time", hlmnc::NC_DOUBLE, {dt}) : -1;
+    r.vv = w.def_var("variable", hlmnc::NC_INT, {dv});
+    w.put_att_text(r.vs, "long_name", "LinkID");
+    if (with_time) {
+        w.put_att_text(r.vt, "long_name", "Time");
+        w.put_att_text(r.vt, "units", "minutes since start of simulation");
+    }
+    w.put_att_text(r.vv, "long_name", "state variable");
+    w.put_att_text(r.vv, "units", "various units");
+    r.vo = with_time ? w.def_var("outputs", out_type, {ds, dt, dv}) : w.def_var("outputs", out_type, {ds, dv});
+    return r;
+}
+}  // namespace hlmnc_detail
+
 /// I_O/output_series.cpp:18-71 — outputs(system,time,variable) with coordinate variables and the
-/// reference's attributes.  compression_level is accepted for signature compatibility and ignored
-/// (classic container).  Errors are printed and swallowed like the reference's NC_CHECK.
+/// reference's attributes; NetCDF-4 with shuffle + deflate(compression_level) on `outputs` as the reference
+/// (compression_level 0: no filter), or the classic container.  Errors are printed and swallowed like the
+/// reference's NC_CHECK.
 inline void write_dense_netcdf(const std::string& filename, const double* h_dense, const double* time_vals,
                                const int* linkid_vals, const int* state_vals, int num_queries, int num_systems, int N_EQ,
-                               int compression_level = 4) {
-    (void)compression_level;
+                               int compression_level = 4, NcFormat format = NcFormat::kNetcdf4) {
     try {
+        if (format == NcFormat::kNetcdf4) {
+            hlmnc::Nc4Writer w(filename);
+            const auto v = hlmnc_detail::define_series(w, num_systems, num_queries, N_EQ, true, hlmnc::NC_DOUBLE);
+            w.def_var_deflate(v.vo, true, compression_level);
+            w.put_var(v.vs, linkid_vals);
+            w.put_var(v.vt, time_vals);
+            w.put_var(v.vv, state_vals);
+            w.put_var(v.vo, h_dense);
+            w.close();
+            return;
+        }
         hlmnc::ClassicWriter w(filename);
-        const int ds = w.def_dim("system", num_systems), dt = w.def_dim("time", num_queries), dv = w.def_dim("variable", N_EQ);
-        const int vs = w.def_var("system", hlmnc::NC_INT, {ds});
-        const int vt = w.def_var("time", hlmnc::NC_DOUBLE, {dt});
-        const int vv = w.def_var("variable", hlmnc::NC_INT, {dv});
-        w.put_att_text(vs, "long_name", "LinkID");
-        w.put_att_text(vt, "long_name", "Time");
-        w.put_att_text(vt, "units", "minutes since start of simulation");
-        w.put_att_text(vv, "long_name", "state variable");
-        w.put_att_text(vv, "units", "various units");
-        const int vo = w.def_var("outputs", hlmnc::NC_DOUBLE, {ds, dt, dv});
+        const auto v = hlmnc_detail::define_series(w, num_systems, num_queries, N_EQ, true, hlmnc::NC_DOUBLE);
         w.enddef();
-        w.put_var(vs, linkid_vals);
-        w.put_var(vt, time_vals);
-        w.put_var(vv, state_vals);
-        w.put_var(vo, h_dense);
+        w.put_var(v.vs, linkid_vals);
+        w.put_var(v.vt, time_vals);
+        w.put_var(v.vv, state_vals);
+        w.put_var(v.vo, h_dense);
         w.close();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "NetCDF error: %s\n", e.what());
@@ -1145,21 +1177,25 @@ inline void write_dense_netcdf(const std::string& filename, const double* h_dens
 
 /// I_O/output_series.cpp:76-123 — outputs(system,variable).
 inline void write_final_netcdf(const std::string& filename, const double* h_y_final, const int* linkid_vals,
-                               const int* state_vals, int num_systems, int N_EQ, int compression_level = 4) {
-    (void)compression_level;
+                               const int* state_vals, int num_systems, int N_EQ, int compression_level = 4,
+                               NcFormat format = NcFormat::kNetcdf4) {
     try {
+        if (format == NcFormat::kNetcdf4) {
+            hlmnc::Nc4Writer w(filename);
+            const auto v = hlmnc_detail::define_series(w, num_systems, 0, N_EQ, false, hlmnc::NC_DOUBLE);
+            w.def_var_deflate(v.vo, true, compression_level);
+            w.put_var(v.vs, linkid_vals);
+            w.put_var(v.vv, state_vals);
+            w.put_var(v.vo, h_y_final);
+            w.close();
+            return;
+        }
         hlmnc::ClassicWriter w(filename);
-        const int ds = w.def_dim("system", num_systems), dv = w.def_dim("variable", N_EQ);
-        const int vs = w.def_var("system", hlmnc::NC_INT, {ds});
-        const int vv = w.def_var("variable", hlmnc::NC_INT, {dv});
-        w.put_att_text(vs, "long_name", "LinkID");
-        w.put_att_text(vv, "long_name", "state variable");
-        w.put_att_text(vv, "units", "various units");
-        const int vo = w.def_var("outputs", hlmnc::NC_DOUBLE, {ds, dv});
+        const auto v = hlmnc_detail::define_series(w, num_systems, 0, N_EQ, false, hlmnc::NC_DOUBLE);
         w.enddef();
-        w.put_var(vs, linkid_vals);
-        w.put_var(vv, state_vals);
-        w.put_var(vo, h_y_final);
+        w.put_var(v.vs, linkid_vals);
+        w.put_var(v.vv, state_vals);
+        w.put_var(v.vo, h_y_final);
         w.close();
     } catch (const std::exception& e) {
         std::fprintf(stderr, "NetCDF error: %s\n", e.what());
@@ -1171,31 +1207,49 @@ inline void write_final_netcdf(const std::string& filename, const double* h_y_fi
 /// Two source layouts: records of all n_eq states, of which the writer picks its own (the default), or — after
 /// set_packed_source() — records the DEVICE already cut down to the selected states in ascending state order
 /// (hlm_set_output_states), as double or float (hlm_set_output_precision; the file variable is then NC_FLOAT).
-/// Rows are scattered into a shared mapping of the file, so a window costs one pass over its own bytes.
+/// Two containers:
+///   * classic: rows are scattered into a shared mapping of the file, so a window costs one pass over its bytes;
+///   * NetCDF-4 (the reference's, default): `outputs` is chunked (systems x queries x all variables) with shuffle +
+///     deflate like the reference's; windows fill a staging slab of one chunk-row of queries, and a complete slab is
+///     compressed chunk by chunk on the host's threads and appended — the file never exists uncompressed.  A series
+///     that fits one 4 MiB chunk is a single chunk, as in the reference's files.
 class DenseSeriesWriter {
   public:
     DenseSeriesWriter(const std::string& filename, const std::vector<double>& time_vals, const std::vector<int>& linkid_vals,
-                      const std::vector<int>& state_vals, int n_eq, bool store_float = false)
-        : w_(filename), nq_(time_vals.size()), ns_(linkid_vals.size()), n_eq_(n_eq), states_(state_vals), f32_(store_float) {
+                      const std::vector<int>& state_vals, int n_eq, bool store_float = false, NcFormat format = NcFormat::kNetcdf4,
+                      int compression_level = 4, uint64_t staging_bytes = 256ULL << 20)
+        : nq_(time_vals.size()), ns_(linkid_vals.size()), n_eq_(n_eq), states_(state_vals), f32_(store_float) {
         for (int s : states_)
             if (s < 0 || s >= n_eq) throw std::runtime_error("output state index out of range");
         src_cols_ = states_;
         src_stride_ = (uint64_t)n_eq;
-        const int ds = w_.def_dim("system", ns_), dt = w_.def_dim("time", nq_), dv = w_.def_dim("variable", states_.size());
-        const int vs = w_.def_var("system", hlmnc::NC_INT, {ds});
-        const int vt = w_.def_var("time", hlmnc::NC_DOUBLE, {dt});
-        const int vv = w_.def_var("variable", hlmnc::NC_INT, {dv});
-        w_.put_att_text(vs, "long_name", "LinkID");
-        w_.put_att_text(vt, "long_name", "Time");
-        w_.put_att_text(vt, "units", "minutes since start of simulation");
-        w_.put_att_text(vv, "long_name", "state variable");
-        w_.put_att_text(vv, "units", "various units");
-        vo_ = w_.def_var("outputs", f32_ ? hlmnc::NC_FLOAT : hlmnc::NC_DOUBLE, {ds, dt, dv});
-        w_.enddef();
-        w_.put_var(vs, linkid_vals.data());
-        w_.put_var(vt, time_vals.data());
-        w_.put_var(vv, states_.data());
-        out_ = w_.map_var(vo_);
+        const int out_type = f32_ ? hlmnc::NC_FLOAT : hlmnc::NC_DOUBLE;
+        const uint64_t nv = states_.size(), es = f32_ ? 4 : 8;
+        if (format == NcFormat::kClassic) {
+            w_.reset(new hlmnc::ClassicWriter(filename));
+            const auto v = hlmnc_detail::define_series(*w_, ns_, nq_, nv, true, out_type);
+            vo_ = v.vo;
+            w_->enddef();
+            w_->put_var(v.vs, linkid_vals.data());
+            w_->put_var(v.vt, time_vals.data());
+            w_->put_var(v.vv, states_.data());
+            out_ = w_->map_var(vo_);
+            return;
+        }
+        n4_.reset(new hlmnc::Nc4Writer(filename));
+        const auto v = hlmnc_detail::define_series(*n4_, ns_, nq_, nv, true, out_type);
+        vo_ = v.vo;
+        // chunk = (cs systems, cq queries, all variables): cq queries of every system must fit the staging slab, a chunk
+        // aims at netcdf-c's 4 MiB default; one chunk when the whole series fits
+        const uint64_t per_q = std::max<uint64_t>(ns_ * nv * es, 1);
+        cq_ = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(nq_, 1), staging_bytes / per_q));
+        cs_ = std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint64_t>(ns_, 1), hlmnc::Nc4Writer::kDefaultChunkBytes / std::max<uint64_t>(cq_ * nv * es, 1)));
+        n4_->def_var_deflate(vo_, true, compression_level, {cs_, cq_, std::max<uint64_t>(nv, 1)});
+        n4_->put_var(v.vs, linkid_vals.data());
+        n4_->put_var(v.vt, time_vals.data());
+        n4_->put_var(v.vv, states_.data());
+        slab_.resize(ns_ * cq_ * nv * es);
+        hlmnc::Nc4Writer::fill_with_default(out_type, slab_.data(), ns_ * cq_ * nv);
     }
     /// The source records hold only the distinct selected states, ascending (what the device writes under
     /// hlm_set_output_states(output_mask())); values are float when the writer stores float.
@@ -1215,36 +1269,95 @@ class DenseSeriesWriter {
         return m;
     }
     /// win = [ns][q_hi - q_lo][source record] (row pitch given in queries) holding queries [q_lo, q_hi);
-    /// values are double, or float for a packed float source
+    /// values are double, or float for a packed float source.  Windows arrive in ascending, gap-free order.
     void write_window(const void* win, uint64_t q_lo, uint64_t q_hi, uint64_t pitch_q) {
         if (q_hi > nq_ || q_lo > q_hi) throw std::out_of_range("dense window outside the query range");
         const uint64_t nv = states_.size();
         const bool src_f32 = packed_ && f32_;
         const int es = f32_ ? 4 : 8;
-        for (uint64_t s = 0; s < ns_; ++s)
-            for (uint64_t q = q_lo; q < q_hi; ++q) {
-                const uint64_t rec = (s * pitch_q + (q - q_lo)) * src_stride_;
-                uint8_t* dst = out_ + ((s * nq_ + q) * nv) * es;
-                for (uint64_t v = 0; v < nv; ++v) {
-                    if (src_f32) {
-                        hlmnc::ClassicWriter::store_be(dst + 4 * v, static_cast<const float*>(win) + rec + src_cols_[v], 4, 1);
-                    } else if (f32_) {
-                        const float x = (float)static_cast<const double*>(win)[rec + src_cols_[v]];
-                        hlmnc::ClassicWriter::store_be(dst + 4 * v, &x, 4, 1);
-                    } else {
-                        hlmnc::ClassicWriter::store_be(dst + 8 * v, static_cast<const double*>(win) + rec + src_cols_[v], 8, 1);
-                    }
+        auto put = [&](uint8_t* dst, uint64_t rec, bool big_endian) {
+            for (uint64_t v = 0; v < nv; ++v) {
+                if (src_f32) {
+                    const float* p = static_cast<const float*>(win) + rec + src_cols_[v];
+                    if (big_endian) hlmnc::ClassicWriter::store_be(dst + 4 * v, p, 4, 1);
+                    else std::memcpy(dst + 4 * v, p, 4);
+                } else if (f32_) {
+                    const float x = (float)static_cast<const double*>(win)[rec + src_cols_[v]];
+                    if (big_endian) hlmnc::ClassicWriter::store_be(dst + 4 * v, &x, 4, 1);
+                    else std::memcpy(dst + 4 * v, &x, 4);
+                } else {
+                    const double* p = static_cast<const double*>(win) + rec + src_cols_[v];
+                    if (big_endian) hlmnc::ClassicWriter::store_be(dst + 8 * v, p, 8, 1);
+                    else std::memcpy(dst + 8 * v, p, 8);
                 }
             }
+        };
+        if (w_) {
+            for (uint64_t s = 0; s < ns_; ++s)
+                for (uint64_t q = q_lo; q < q_hi; ++q)
+                    put(out_ + ((s * nq_ + q) * nv) * es, (s * pitch_q + (q - q_lo)) * src_stride_, true);
+            return;
+        }
+        if (q_lo != q_next_) throw std::runtime_error("NetCDF-4 dense writer: windows must arrive in order, without gaps");
+        for (uint64_t qa = q_lo; qa < q_hi;) {  // the part of the window inside the current chunk-row of queries
+            const uint64_t row = qa / cq_, qb = std::min(q_hi, (row + 1) * cq_);
+            for (uint64_t s = 0; s < ns_; ++s)
+                for (uint64_t q = qa; q < qb; ++q)
+                    put(slab_.data() + ((s * cq_ + (q - row * cq_)) * nv) * es, (s * pitch_q + (q - q_lo)) * src_stride_, false);
+            qa = qb;
+            q_next_ = qb;
+            if (qb == (row + 1) * cq_ || qb == nq_) flush_slab(row);
+        }
     }
-    void close() { w_.close(); }
+    void close() {
+        if (w_) w_->close();
+        if (n4_) n4_->close();
+    }
 
   private:
-    hlmnc::ClassicWriter w_;
+    // compress the chunks of one chunk-row (all systems x cq_ queries) on the host's threads, append them in order
+    void flush_slab(uint64_t row) {
+        const uint64_t nv = states_.size(), es = f32_ ? 4 : 8;
+        const uint64_t n_chunks = (ns_ + cs_ - 1) / cs_, chunk_bytes = cs_ * cq_ * nv * es;
+        const int out_type = f32_ ? hlmnc::NC_FLOAT : hlmnc::NC_DOUBLE;
+        std::vector<std::vector<uint8_t>> enc(n_chunks);
+        const unsigned n_thr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)std::max(1u, std::thread::hardware_concurrency()), n_chunks, (uint64_t)32}));
+        std::vector<std::thread> pool;
+        std::string err;
+        for (unsigned t = 0; t < n_thr; ++t)
+            pool.emplace_back([&, t] {
+                try {
+                    std::vector<uint8_t> padded;
+                    for (uint64_t c = t; c < n_chunks; c += n_thr) {
+                        const uint64_t s0 = c * cs_, n_s = std::min(cs_, ns_ - s0);
+                        const uint8_t* src = slab_.data() + s0 * cq_ * nv * es;
+                        if (n_s < cs_) {  // the last chunk overhangs the system dimension: pad with the fill value
+                            padded.resize(chunk_bytes);
+                            hlmnc::Nc4Writer::fill_with_default(out_type, padded.data(), cs_ * cq_ * nv);
+                            std::memcpy(padded.data(), src, n_s * cq_ * nv * es);
+                            src = padded.data();
+                        }
+                        n4_->encode_chunk(vo_, src, enc[c]);
+                    }
+                } catch (const std::exception& e) {
+                    err = e.what();
+                }
+            });
+        for (auto& th : pool) th.join();
+        if (!err.empty()) throw std::runtime_error(err);
+        for (uint64_t c = 0; c < n_chunks; ++c) n4_->put_encoded_chunk(vo_, {c, row, 0}, enc[c]);
+        hlmnc::Nc4Writer::fill_with_default(out_type, slab_.data(), ns_ * cq_ * nv);  // queries past nq_ in the last row stay fill
+    }
+
+    std::unique_ptr<hlmnc::ClassicWriter> w_;
+    std::unique_ptr<hlmnc::Nc4Writer> n4_;
     uint64_t nq_, ns_;
     int n_eq_, vo_ = -1;
     std::vector<int> states_, src_cols_;
     uint64_t src_stride_ = 0;
     bool f32_ = false, packed_ = false;
     uint8_t* out_ = nullptr;
+    // NetCDF-4: chunk shape (cs_ systems x cq_ queries x all variables), staging slab [ns][cq_][nv], next query expected
+    uint64_t cs_ = 1, cq_ = 1, q_next_ = 0;
+    std::vector<uint8_t> slab_;
 };

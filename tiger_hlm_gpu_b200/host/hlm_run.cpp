@@ -308,6 +308,7 @@ int run(const Options& opt) {
     const std::string out_dir = join_path(root, cfg.output.dir);
     const std::string suffix = "_rank_" + std::to_string(opt.rank);
     const bool csv = cfg.output.format == "csv";
+    const NcFormat nc_format = cfg.output.format == "netcdf3" ? NcFormat::kClassic : NcFormat::kNetcdf4;
     std::unique_ptr<DenseSeriesWriter> dense_writer;
     std::vector<double> dense_all;  // csv only
     // NetCDF output: output.states and output.precision are applied where the records are produced — the window
@@ -317,7 +318,8 @@ int run(const Options& opt) {
     size_t rec_elem = sizeof(double);
     if (cfg.output.dense && !csv) {
         const bool f32 = cfg.output.precision == 32;
-        dense_writer.reset(new DenseSeriesWriter(out_dir + "/" + cfg.output.prefix + "dense" + suffix + ".nc", tq, linkids, states, n_eq, f32));
+        dense_writer.reset(new DenseSeriesWriter(out_dir + "/" + cfg.output.prefix + "dense" + suffix + ".nc", tq, linkids, states, n_eq, f32,
+                                                 nc_format, cfg.output.compression_level));
         dense_writer->set_packed_source();
         check(hlm_set_output_states(ctx, dense_writer->output_mask()), "hlm_set_output_states");
         check(hlm_set_output_precision(ctx, f32 ? 32 : 64), "hlm_set_output_precision");
@@ -422,7 +424,8 @@ int run(const Options& opt) {
         write_final_csv(out_dir + "/" + cfg.output.prefix + "final" + suffix + ".csv", y_final, (int)ns, n_eq);
         if (cfg.output.dense) write_dense_csv(out_dir + "/" + cfg.output.prefix + "dense" + suffix + ".csv", dense_all, tq, (int)ns, n_eq);
     } else {
-        write_final_netcdf(out_dir + "/" + cfg.output.prefix + "final" + suffix + ".nc", y_final.data(), linkids.data(), all_states.data(), (int)ns, n_eq, 0);
+        write_final_netcdf(out_dir + "/" + cfg.output.prefix + "final" + suffix + ".nc", y_final.data(), linkids.data(), all_states.data(), (int)ns, n_eq,
+                           cfg.output.compression_level, nc_format);
         if (dense_writer) dense_writer->close();
     }
     long long acc = 0, rej = 0, jump = 0, stiff = 0, stalled = 0, solved = 0;
