@@ -363,10 +363,15 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
     rs = routing.RoutedSolver(solver, 200, topo, world, plan.max_send, dist, exchange=args.exchange)
     stream = rs.stream
 
+    # hourly output like the other workloads, and of the routed quantity: one record of the channel discharge per link
+    # at the end of the hour's last coupling interval (hlm_set_output_states: only that state is interpolated and stored)
+    solver.set_output_states([0])
+    no_tq = np.zeros(0)
+
     def hour(k, first=False):
         for i in range(n_int):
             tf = 60.0 * k + dt * (i + 1)
-            tq = np.array([tf])
+            tq = np.array([tf]) if i == n_int - 1 else no_tq
             if first and i == 0:
                 rs.begin(y0, 0.0, tf, tq)
             rs.advance(tf, tq)
@@ -400,11 +405,11 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
     state = dict(tot1)
 
     # e2e: the same intervals, with the host in the loop as a caller writing hourly output has it: the hour's
-    # last dense record (discharge + stores of every link) is copied to pinned host memory every step, and the
-    # first step uploads y0.  (Between intervals nothing else crosses PCIe: state stays resident.)
+    # discharge record of every link is copied to pinned host memory every step, and the first step uploads y0.
+    # (Between intervals nothing else crosses PCIe: state stays resident.)
     e2e = None
     if with_e2e:
-        win = torch.zeros((sel.size, 1, 5), dtype=torch.float64).pin_memory()
+        win = torch.zeros((sel.size, 1, 1), dtype=torch.float64).pin_memory()
         env.barrier()
         t_start = time.perf_counter()
         acc_before = solver.solve_totals()["n_accept"]
@@ -416,7 +421,7 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
         acc_e = solver.solve_totals()["n_accept"] - acc_before
         e_ms_max, (acc_e_all,) = env.reduce(e_ms, [acc_e])
         e2e = {"value": acc_e_all / (e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_int,
-               "d2h_bytes_per_step": int(sel.size) * 40 + 56, "ms_per_step": e_ms_max / K,
+               "d2h_bytes_per_step": int(sel.size) * 8 + 56, "ms_per_step": e_ms_max / K,
                "api": "routing.RoutedSolver over the C ABI (hlm_route_gather + hlm_solve_advance + hlm_solve_window + "
                       "hlm_solve_fetch_window_packed), pinned host buffer; state resident between intervals"}
     peer = rs.peer
@@ -440,6 +445,8 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
                    "links_per_gpu": links_per_gpu, "links_total": ns_all, "couple_minutes": dt,
                    "intervals_per_step": n_int, "schedule": args.schedule, "sub_basins": plan.n_subbasins, "cut_edges": plan.n_cut_edges,
                    "halo_doubles": plan.halo_len, "rtol": PRM6[1], "atol": PRM6[2],
+                   "output": "hourly channel discharge of every link (state 0), interpolated at the hour by the last interval's launch",
+                   "reject_limit": routing.ROUTED_REJECT_LIMIT,
                    "parallelism": (f"sub-basins dealt to {world} GPU(s); " +
                                    ("boundary discharge stored into peer memory by the kernels, one barrier per interval" if peer
                                     else "one NCCL all-gather of the boundary vector per interval"))

@@ -121,6 +121,13 @@ int hlm_clear_forcings(hlm_ctx* ctx);
 
 /* Attempt budget per link per window launch; <= 0 = unbounded like the reference.  Default 0. */
 int hlm_set_max_attempts(hlm_ctx* ctx, long long per_link);
+/* How many consecutive rejected attempts flag a link stiff: more than `n`.  Default 5, the reference's rule
+ * (`reject_count > 5`, solver/rk45_kernel.cu:160).  The rule doubles as a kink detector: across a switch of one of the
+ * model's min/max terms the error estimate falls like h, not h^5, and the controller needs a run of 6-8 rejections
+ * to get past — not stiffness.  Routed runs, where one abandoned link starves everything downstream and the
+ * implicit fallback costs a serial chain of Newton solves per interval, raise it (20) and leave true stiffness to
+ * the other test, h < (tf - t0) * 1e-6. */
+int hlm_set_reject_limit(hlm_ctx* ctx, int n);
 /* Bytes of device memory one dense-output window buffer may take (two are allocated when the run
  * needs more than one window).  Default 8 GiB. */
 int hlm_set_dense_window_bytes(hlm_ctx* ctx, long long bytes);

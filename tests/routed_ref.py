@@ -31,7 +31,8 @@ class OracleRank:
 
     def advance(self, tf, tq):
         r = O.run_rk45(200, self.prm, self.y, self.t_end, tf, tq, sp=self.sp, forcing=self.forcing,
-                       inflow=self.qin, state_io=(self.t, self.h), stiff_fallback=True, **self.kw)
+                       inflow=self.qin, state_io=(self.t, self.h), stiff_fallback=True,
+                       reject_limit=routing.ROUTED_REJECT_LIMIT, **self.kw)
         assert np.isin(r["stiff"], (0, 3)).all()     # 3 = flagged by the RK45 loop, finished by the implicit fallback
         self.y = r["final"]
         self.t_end = tf

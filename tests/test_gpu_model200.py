@@ -160,6 +160,7 @@ def test_two_ranks_on_one_gpu_equal_one_rank_bit_for_bit():
             upload(s, sp[sel], col[sel], pr, t2m)
             s.route_set_topology(topo.up_ptr, topo.up_idx, topo.send_idx)
             s.set_stiff_fallback(True)
+            s.set_reject_limit(routing.ROUTED_REJECT_LIMIT)  # what RoutedSolver sets, and routed_ref uses
             # each context writes straight into its segment of the "gathered" vector
             s.route_set_send_buffer(halo.data_ptr() + 8 * topo.rank * p2.max_send)
             ctxs.append((s, topo, sel))

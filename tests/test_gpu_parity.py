@@ -326,6 +326,16 @@ def test_errors_are_loud(solver):
     solver.clear_forcings()
     with pytest.raises(HlmError, match="exactly ns SpatialParams"):
         solver.run_rk45(204, np.ones((11, 5)), 0.0, 1.0, None)
+    # a forcing column outside the arrays would be an out-of-bounds device read: refused on the host
+    solver.upload_forcing(0, 1.0, np.zeros((3, 4), np.float32))
+    with pytest.raises(HlmError, match="column 4"):
+        solver.set_forcing_columns(np.array([0, 1, 4, 2, 0, 0, 0, 0, 0, 0], np.int32))
+    with pytest.raises(HlmError, match="negative column"):
+        solver.set_forcing_columns(np.array([0, -1], np.int32))
+    solver.set_forcing_columns(np.array([0, 1, 3, 2, 0, 0, 0, 0, 0, 0], np.int32))
+    with pytest.raises(HlmError, match="refers to column 3"):
+        solver.upload_forcing(0, 1.0, np.zeros((3, 3), np.float32))
+    solver.clear_forcings()
 
 
 # ---- resident session, partition invariance, FP32 ---------------------------------------------------

@@ -50,6 +50,7 @@ SIGNATURES = {
     "hlm_clear_forcings": (_I, [_V]),
     "hlm_set_max_attempts": (_I, [_V, _LL]),
     "hlm_set_dense_window_bytes": (_I, [_V, _LL]),
+    "hlm_set_reject_limit": (_I, [_V, _I]),
     "hlm_set_precision": (_I, [_V, _I]),
     "hlm_set_output_states": (_I, [_V, C.c_uint]),
     "hlm_set_output_precision": (_I, [_V, _I]),
@@ -239,6 +240,10 @@ class Solver:
 
     def set_max_attempts(self, n: int):
         _check(self._lib.hlm_set_max_attempts(self._h, n))
+
+    def set_reject_limit(self, n: int = 5):
+        """More than n consecutive rejections flag a link stiff (5 = the reference's rule)."""
+        _check(self._lib.hlm_set_reject_limit(self._h, n))
 
     def set_dense_window_bytes(self, n: int):
         _check(self._lib.hlm_set_dense_window_bytes(self._h, n))

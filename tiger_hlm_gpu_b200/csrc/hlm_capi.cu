@@ -8,6 +8,7 @@
 // results land directly in the caller's [link][query][state] layout, and long runs are cut into
 // query windows whose D2H copy overlaps the next window's integration.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -107,6 +108,7 @@ struct hlm_ctx {
     std::vector<cudaEvent_t> chunk_ready;
     std::map<int, hlm::SolverParams> params;
     long long max_attempts = 0;
+    int reject_limit = 5;  // solver/rk45_kernel.cu:160
     long long dense_window_bytes = 8LL << 30;
     int precision = 64;
     unsigned int out_mask = 0;  // states a dense record carries (0 = all), hlm_set_output_states
@@ -129,6 +131,7 @@ struct hlm_ctx {
     int n_forc = 0;
     DevBuf<int> forc_col;
     long long forc_col_n = 0;  // 0 = identity
+    long long forc_col_min = 0, forc_col_max = -1;  // range of the map's entries (checked against forc_ncols)
 
     // session
     bool in_session = false;
@@ -155,6 +158,11 @@ struct hlm_ctx {
     DevBuf<unsigned int> radau_count, n_radau;
 
     int schedule = HLM_SCHEDULE_AUTO;
+    // lane-refill schedule, longest first: attempts per link of the last launch -> order of the next (dispatch_window)
+    DevBuf<int> cost, cost_sorted, iota, order;
+    DevBuf<unsigned char> sort_tmp;
+    long long cost_ns = 0;  // links the costs were recorded for (0 = none yet)
+    bool longest_first = true;
 
     // routed runs (models with upstream inflow): topology of the links this context owns
     bool routed = false;
@@ -294,6 +302,11 @@ __global__ void totals_kernel(const unsigned int* __restrict__ n_acc, const unsi
     }
 }
 
+__global__ void iota_kernel(int* __restrict__ p, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int)i;
+}
+
 // Register-resident FMA throughput probe: 8 independent chains per thread.
 template <typename T> __global__ void fma_peak_kernel(T* out, int iters, T seed) {
     T a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
@@ -401,7 +414,7 @@ cudaEvent_t get_event(hlm_ctx* c) {
 // by default lanes where links take unlike numbers of attempts per launch — Model 200 (the channel's pace grows
 // with its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
 // tiles otherwise.  The kernels live in rk45_instance.cu, one translation unit per (model, number type).
-int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
+int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     using Launcher = cudaError_t (*)(int, const hlm::WindowArgs&, int, cudaStream_t);
     Launcher launch = nullptr;
     bool divergent_model = false;
@@ -411,7 +424,44 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a) {
     else if (c->uid == hlm::DummyModel::UID) launch = f32 ? hlm::launch_rk45_dummy_f32 : hlm::launch_rk45_dummy_f64;
     else return fail(HLM_ERR_INVALID, "unknown model uid");
     const bool lanes = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && (c->routed || divergent_model));
+    hlm::WindowArgs a = a_in;
+    // Longest first.  Under lane refill a launch ends with the lanes that drew a long link late while the others have
+    // run out of links (22 of 32 threads active on the routed workload).  A link's attempt count changes slowly from
+    // one launch to the next, so the launch deals the links in the order of the attempts they took last time, most
+    // first.  One stable 4-bit radix pass (attempts / 4, up to 60): links with like counts keep their ascending order,
+    // so neighbouring lanes still touch neighbouring memory.  Only for launches over all links of the session.
+    if (lanes && c->longest_first && !f32 && a.tile_lo == 0 && a.n_tiles == (c->ns + 31) / 32 && c->ns < (1LL << 31)) {
+        const size_t n = (size_t)c->ns;
+        HLM_CUDA(c->cost.reserve((size_t)c->ld));
+        if (c->cost_ns == c->ns) {
+            HLM_CUDA(c->cost_sorted.reserve(n));
+            HLM_CUDA(c->order.reserve(n));
+            if (c->iota.cap < n) {
+                HLM_CUDA(c->iota.reserve(n));
+                iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->iota.p, (long long)n);
+                HLM_CUDA(cudaGetLastError());
+                ++c->launches;
+            }
+            size_t tmp_bytes = 0;
+            HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
+                                                               (int)n, 2, 6, c->stream));
+            HLM_CUDA(c->sort_tmp.reserve(tmp_bytes));
+            HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->sort_tmp.p, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
+                                                               (int)n, 2, 6, c->stream));
+            c->launches += 3;  // histogram, scan, one scatter pass
+            a.order = c->order.p;
+        }
+        a.cost = c->cost.p;
+        c->cost_ns = c->ns;
+    }
     HLM_CUDA(cudaMemsetAsync(c->tile_counter.p, 0, sizeof(unsigned int), c->stream));
+    // per-launch timing for hlm_kernel_time_ms: a caller that never asks (a routed run queues ~10^5 launches a year)
+    // must not accumulate events — beyond a bound the oldest pair is recycled
+    if (c->timing.size() >= 1024) {
+        c->event_pool.push_back(c->timing.front().first);
+        c->event_pool.push_back(c->timing.front().second);
+        c->timing.erase(c->timing.begin());
+    }
     cudaEvent_t e0 = get_event(c), e1 = get_event(c);
     HLM_CUDA(cudaEventRecord(e0, c->stream));
     // routed runs take a few attempts per link per launch: the lane kernel that tests for "finished" right
@@ -478,10 +528,16 @@ void hlm_destroy(hlm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    // every device buffer of the context (a process that creates and destroys contexts must not leak)
+    c->io_stage.release();
     c->sp_aos.release(); c->sp_soa.release(); c->forc[0].release(); c->forc[1].release(); c->forc_col.release();
     c->y.release(); c->t.release(); c->h.release(); c->tq.release(); c->next_q.release(); c->reject_run.release();
     c->status.release(); c->n_acc.release(); c->n_rej.release(); c->n_jump.release(); c->tile_counter.release();
     c->totals.release(); c->dense[0].release(); c->dense[1].release();
+    c->radau_list.release(); c->radau_count.release(); c->n_radau.release();
+    c->cost.release(); c->cost_sorted.release(); c->iota.release(); c->order.release(); c->sort_tmp.release();
+    c->up_ptr.release(); c->up_idx.release(); c->send_idx.release(); c->send_slot.release(); c->qin.release(); c->own_send.release();
+    c->peer_ptrs.release();
     for (auto& p : c->timing) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -565,6 +621,9 @@ int hlm_upload_forcing_chunk(hlm_ctx* c, int j, double dt_hours, long long nT_to
     for (int k = 0; k < c->n_forc; ++k)
         if (k != j && c->forc_ncols != ncols)
             return fail(HLM_ERR_INVALID, "hlm_upload_forcing: all forcings must share ncols");
+    if (c->forc_col_n != 0 && c->forc_col_max >= ncols)
+        return fail(HLM_ERR_INVALID, "hlm_upload_forcing: the forcing column map refers to column " + std::to_string(c->forc_col_max) +
+                                         " but this forcing has " + std::to_string(ncols) + " columns");
     if (int r = use_device(c)) return r;
     // a larger chunk reallocates: the window kernels queued on the stream must be done with the old buffer
     if ((size_t)nT_chunk * ncols > c->forc[j].cap) HLM_CUDA(cudaStreamSynchronize(c->stream));
@@ -586,6 +645,18 @@ int hlm_upload_forcing(hlm_ctx* c, int j, double dt_hours, long long nT, long lo
 int hlm_set_forcing_columns(hlm_ctx* c, const int* col, long long n) {
     HLM_REQUIRE(c, "hlm_set_forcing_columns: ctx is NULL");
     if (!col || n == 0) { c->forc_col_n = 0; return HLM_OK; }
+    // a column outside the forcing arrays would be an out-of-bounds device read in every kernel
+    long long lo = col[0], hi = col[0];
+    for (long long i = 1; i < n; ++i) {
+        lo = std::min<long long>(lo, col[i]);
+        hi = std::max<long long>(hi, col[i]);
+    }
+    if (lo < 0) return fail(HLM_ERR_INVALID, "hlm_set_forcing_columns: negative column index");
+    if (c->n_forc > 0 && hi >= c->forc_ncols)
+        return fail(HLM_ERR_INVALID, "hlm_set_forcing_columns: column " + std::to_string(hi) + " but the forcings have " +
+                                         std::to_string(c->forc_ncols) + " columns");
+    c->forc_col_min = lo;
+    c->forc_col_max = hi;
     if (int r = use_device(c)) return r;
     const long long ld = (n + 31) / 32 * 32;
     HLM_CUDA(c->forc_col.reserve((size_t)ld));
@@ -606,6 +677,12 @@ int hlm_clear_forcings(hlm_ctx* c) {
 int hlm_set_max_attempts(hlm_ctx* c, long long v) {
     HLM_REQUIRE(c, "hlm_set_max_attempts: ctx is NULL");
     c->max_attempts = v;
+    return HLM_OK;
+}
+
+int hlm_set_reject_limit(hlm_ctx* c, int n) {
+    HLM_REQUIRE(c && n >= 0, "hlm_set_reject_limit: need n >= 0");
+    c->reject_limit = n;
     return HLM_OK;
 }
 
@@ -700,6 +777,9 @@ static int solve_begin_impl(hlm_ctx* c, int uid, const double* y0, long long ns,
         return fail(HLM_ERR_INVALID, "hlm_solve_begin: forcing has fewer columns than links and no column map");
     if (m->n_forc > 0 && c->forc_col_n != 0 && c->forc_col_n != ns)
         return fail(HLM_ERR_INVALID, "hlm_solve_begin: forcing column map length differs from ns");
+    if (m->n_forc > 0 && c->n_forc > 0 && c->forc_col_n != 0 && c->forc_col_max >= c->forc_ncols)
+        return fail(HLM_ERR_INVALID, "hlm_solve_begin: the forcing column map refers to column " + std::to_string(c->forc_col_max) +
+                                         " but the forcings have " + std::to_string(c->forc_ncols) + " columns");
     if (int r = use_device(c)) return r;
     // a previous call's D2H copies may still read the window buffers
     HLM_CUDA(cudaStreamSynchronize(c->copy_stream));
@@ -715,6 +795,7 @@ static int solve_begin_impl(hlm_ctx* c, int uid, const double* y0, long long ns,
     c->q_done = 0;
     c->win_q_lo = c->win_q_hi = 0;
     c->win_has_dense = false;
+    c->cost_ns = 0;  // no attempt counts yet for these links
     const size_t ld = (size_t)c->ld;
     HLM_CUDA(c->y.reserve(ld * m->n_eq));
     HLM_CUDA(c->t.reserve(ld));
@@ -846,6 +927,7 @@ static int queue_window(hlm_ctx* c, long long q_lo, long long q_hi, void* dense,
     a.ns = c->ns; a.ld = c->ld;
     a.tile_lo = tile_lo; a.n_tiles = n_tiles; a.dense_sys0 = dense_sys0;
     a.max_attempts = c->max_attempts;
+    a.reject_limit = c->reject_limit;
     a.tile_counter = c->tile_counter.p;
     if (c->routed) {
         if (c->route_ns != c->ns) return fail(HLM_ERR_STATE, "hlm_solve_window: routing topology was set for another link count");

@@ -160,6 +160,12 @@ struct WindowArgs {
     // then leaves in one contiguous copy)
     long long tile_lo, n_tiles, dense_sys0;
     long long max_attempts;  // per link per launch; <=0 = unbounded like the reference
+    int reject_limit;        // more consecutive rejections than this flag the link stiff (5: rk45_kernel.cu:160)
+    // Lane-refill schedule, longest first: `order` (or nullptr = ascending) lists the launch's links by the attempts
+    // they took in the previous launch, most first, so that the long links start early and the launch's tail is made
+    // of short ones; `cost` (or nullptr) receives the attempts each link takes in this launch.
+    const int* order;        // [links of the launch] link indices
+    int* cost;               // [ld]
     unsigned int* tile_counter;
     // routed models (Model::HAS_INFLOW): discharge entering each link from upstream, constant over the
     // interval (nullptr = unrouted, 0); and, for links another rank needs, where the epilogue puts the
@@ -412,7 +418,7 @@ template <class Model, typename T> struct LinkRun {
     T y[N], k[7][N], y_next[N];
     T t, h, tq_next;
     int next_q, reject_run, status, budget;
-    unsigned int n_acc, n_rej, n_jmp;
+    unsigned int n_acc, n_rej, n_jmp, n_at_load;
     typename Model::template Link<T> L;
     bool fast_ok, k0_valid;
     T F[2];
@@ -430,6 +436,7 @@ template <class Model, typename T> struct LinkRun {
         n_acc = a.n_accept[sys];
         n_rej = a.n_reject[sys];
         n_jmp = a.n_jump[sys];
+        n_at_load = n_acc + n_rej + n_jmp;
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
         fast_ok = Model::template fast_div_ok<T>(L) && f::fast_params_ok((T)a.prm.rtol, (T)a.prm.atol);
@@ -489,6 +496,7 @@ template <class Model, typename T> struct LinkRun {
         a.n_accept[sys] = n_acc;
         a.n_reject[sys] = n_rej;
         a.n_jump[sys] = n_jmp;
+        if (a.cost != nullptr) a.cost[sys] = (int)min(n_acc + n_rej + n_jmp - n_at_load, 63u);  // the sort reads 6 bits
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
@@ -528,12 +536,16 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_lanes
                 const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
                 if (idx >= n_links) {
                     exhausted = true;
-                } else if (a.status[first + idx] == kActive) {
-                    r.status = kActive;
-                    r.load(a, first + idx);
-                    have = true;
                 } else {
-                    dense_zero(a, first + idx, a.q_lo, a.q_hi);
+                    const long long sys = a.order != nullptr ? (long long)__ldg(a.order + idx) : first + idx;
+                    if (a.status[sys] == kActive) {
+                        r.status = kActive;
+                        r.load(a, sys);
+                        have = true;
+                    } else {
+                        if (a.cost != nullptr) a.cost[sys] = 0;
+                        dense_zero(a, sys, a.q_lo, a.q_hi);
+                    }
                 }
             }
         }

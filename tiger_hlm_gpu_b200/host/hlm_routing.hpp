@@ -189,6 +189,10 @@ inline RoutePlan plan_routes(const std::vector<long long>& stream, const std::ve
 /// collective on device buffers (ncclAllGather on the context's stream, or MPI for a CUDA-aware build) — or, in
 /// peer mode (hlm_route_peer_*), just a barrier; it is not called when world == 1 or nothing crosses ranks.  The implicit fallback is switched on for the run: a
 /// link the explicit path abandons would freeze and starve everything downstream.
+/// consecutive rejections before a routed run flags a link stiff (hlm_set_reject_limit; the Python mirror's
+/// routing.ROUTED_REJECT_LIMIT)
+constexpr int kRoutedRejectLimit = 20;
+
 class RoutedRun {
   public:
     using Exchange = std::function<void(const double* d_send, long long n, double* d_halo)>;
@@ -200,6 +204,7 @@ class RoutedRun {
                                      (long long)topo.send_idx.size()),
               "hlm_route_set_topology");
         check(hlm_set_stiff_fallback(ctx.get(), 1), "hlm_set_stiff_fallback");
+        check(hlm_set_reject_limit(ctx.get(), kRoutedRejectLimit), "hlm_set_reject_limit");
         if (world_ > 1 && max_send_ > 0) {
             // with the peer-memory exchange (hlm_route_peer_alloc/open done by the caller) the kernels deliver the
             // data themselves: the callback is then only a barrier on the stream and the two buffers stay null
@@ -210,6 +215,7 @@ class RoutedRun {
     }
     ~RoutedRun() {
         hlm_set_stiff_fallback(ctx_.get(), 0);
+        hlm_set_reject_limit(ctx_.get(), 5);
         hlm_route_clear(ctx_.get());
     }
     /// First interval [t0, tf]; tq = query times inside it.

@@ -297,6 +297,7 @@ int run(const Options& opt) {
             " boundary links, coupling interval " + cfg.routing.couple);
     }
     check(hlm_set_stiff_fallback(ctx, (cfg.solver.stiff_fallback || routed) ? 1 : 0), "hlm_set_stiff_fallback");
+    if (routed) check(hlm_set_reject_limit(ctx, hlm_b200::kRoutedRejectLimit), "hlm_set_reject_limit");
     const double interval = parse_interval_minutes(routed ? cfg.routing.couple : cfg.solver.interval);
     const double chunk = std::max(interval, parse_interval_minutes("30d"));
 

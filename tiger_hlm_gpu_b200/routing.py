@@ -27,6 +27,11 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
+# Routed runs flag a link stiff after more than this many consecutive rejections (the reference's 5 is a kink detector
+# as much as a stiffness test: hlm_b200.h, hlm_set_reject_limit); the CPU routed run (tests/routed_ref.py) uses the same.
+ROUTED_REJECT_LIMIT = 20
+
+
 def downstream_index(stream: np.ndarray, next_stream: np.ndarray) -> np.ndarray:
     """Index of each link's downstream link, -1 for outlets (next_stream not among `stream`)."""
     stream = np.asarray(stream, dtype=np.int64)
@@ -233,6 +238,7 @@ class RoutedSolver:
         solver.set_stream(self.stream.cuda_stream)
         solver.route_set_topology(topo.up_ptr, topo.up_idx, topo.send_idx)
         solver.set_stiff_fallback(True)
+        solver.set_reject_limit(ROUTED_REJECT_LIMIT)
         self.send = self.halo = self.flag = None
         self.peer = exchange == "peer" and world > 1 and max_send > 0
         if exchange not in ("nccl", "peer"):
@@ -291,4 +297,5 @@ class RoutedSolver:
             self.s.route_peer_close()
         self.s.set_stream(None)
         self.s.set_stiff_fallback(False)
+        self.s.set_reject_limit(5)
         return r
