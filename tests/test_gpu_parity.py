@@ -661,3 +661,49 @@ def test_fp32_mode_at_the_bench_tolerances(solver):
                                           f"(FP64 sensitivity to a 10x tolerance change: {sens:.3e})")
     ratio = s["n_accept"].sum() / d["n_accept"].sum()
     assert 0.9 < ratio < 1.1, ratio  # measured 1.00003: the controller is not yet at its noise floor
+
+
+# ---- BASELINE configs[0] / configs[1] at the size of the reference's (absent) small_example_params.csv ----------
+
+N_SMALL_EXAMPLE = 41_274  # rows of data/small_example_pr_lookup.csv: the presumed size of small_example_params.csv
+
+
+def test_dummy_model_at_the_small_example_size(solver, golden_dummy):
+    """C1 at 41 274 systems (the reference's DummyModel run on data/small_example_params.csv): every system is the same
+    ODE from the same y0, so every row must carry the bits of the oracle's single system — and the golden's values."""
+    tq = golden_dummy["query_times"][::50]  # 200 of the 10 000 queries: the dense array stays at 330 MB
+    solver.set_model_parameters(0, Parameters())
+    solver.set_max_attempts(100000)
+    y0 = np.ones((N_SMALL_EXAMPLE, 5))
+    g = solver.run_rk45(0, y0, 0.0, 5.0, tq)
+    o = orun(0, O.Params.make(), y0[:1], 0.0, 5.0, tq)
+    assert not g["stiff"].any()
+    assert np.all(g["n_accept"] == o["n_accept"][0]) and np.all(g["n_reject"] == o["n_reject"][0])
+    assert np.array_equal(g["final"], np.repeat(o["final"], N_SMALL_EXAMPLE, axis=0))
+    assert np.array_equal(g["dense"], np.repeat(o["dense"], N_SMALL_EXAMPLE, axis=0))
+    np.testing.assert_allclose(g["final"][-1], golden_dummy["final_csv"][0], rtol=3e-6)
+
+
+def test_model204_at_the_small_example_size(solver):
+    """C2 at 41 274 links: the reference's run shape (t in [0, 2880] min, 49 hourly queries, main.cpp:610-657) on synthetic
+    parameters and a forcing grid of 88 cells (the cell count of the reference's lookup files), bit for bit against
+    the oracle in every state, dense record and counter."""
+    ns = N_SMALL_EXAMPLE
+    sp = synthetic.make_spatial_params(ns, seed=41)
+    col, ncells = synthetic.make_cells(ns, links_per_cell=470)
+    assert ncells == 88
+    pr, t2m = synthetic.make_forcing_grid(ncells, 2, seed=274)
+    y0 = synthetic.make_y0(ns, wet_fraction=0.2, seed=3)
+    solver.set_model_parameters(204, PRM)
+    solver.set_max_attempts(2_000_000)
+    solver.upload_spatial_params(sp)
+    solver.clear_forcings()
+    solver.upload_forcing(0, 1.0, pr)
+    solver.upload_forcing(1, 24.0, t2m)
+    solver.set_forcing_columns(col)
+    tq = synthetic.hourly_queries(0.0, 2880.0)
+    assert tq.size == 49
+    g = solver.run_rk45(204, y0, 0.0, 2880.0, tq)
+    o = orun(204, OPRM, y0, 0.0, 2880.0, tq, sp=sp, forcing=O.Forcing([pr, t2m], [1.0, 24.0], col=col), threads=os.cpu_count() or 8)
+    assert_same_result(g, o, exact=True)
+    assert (g["stiff"] == 0).sum() > 0.9 * ns

@@ -211,15 +211,21 @@ __device__ __forceinline__ void dense_put(const WindowArgs& a, long long idx, do
     if (a.dense_f32) static_cast<float*>(a.dense)[idx] = (float)v;
     else static_cast<double*>(a.dense)[idx] = v;
 }
-// zero records for queries [q_from, q_to) of link sys (clipped to the window)
-static __device__ __noinline__ void dense_zero(const WindowArgs& a, long long sys, int q_from, int q_to) {
+// zero records for queries [q_from, q_to) of link sys (clipped to the window).  Out of line (it runs for the rare
+// link that leaves queries unreached), and with every argument BY VALUE: a reference to the kernel's parameter
+// struct would force the whole struct into local memory for the kernel's lifetime.
+static __device__ __noinline__ void dense_zero_rows(void* dense, int f32, int ncol, long long first_record, int n_records) {
+    for (long long i = first_record * ncol, end = (first_record + n_records) * ncol; i < end; ++i) {
+        if (f32) static_cast<float*>(dense)[i] = 0.0f;
+        else static_cast<double*>(dense)[i] = 0.0;
+    }
+}
+__device__ __forceinline__ void dense_zero(const WindowArgs& a, long long sys, int q_from, int q_to) {
     if (a.dense == nullptr) return;
     if (q_from < a.q_lo) q_from = a.q_lo;
     if (q_to > a.q_hi) q_to = a.q_hi;
-    for (int q = q_from; q < q_to; ++q) {
-        const long long b = dense_base(a, sys, q);
-        for (int c = 0; c < a.dense_ncol; ++c) dense_put(a, b + c, 0.0);
-    }
+    if (q_to <= q_from) return;
+    dense_zero_rows(a.dense, a.dense_f32, a.dense_ncol, (sys - a.dense_sys0) * (long long)(a.q_hi - a.q_lo) + (q_from - a.q_lo), q_to - q_from);
 }
 
 // One DOPRI5 attempt from (y, k0): fills k[1..6], y_next and the FSAL flag, returns err.
