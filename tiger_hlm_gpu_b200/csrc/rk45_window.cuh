@@ -544,9 +544,14 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_lanes
                     exhausted = true;
                 } else {
                     const long long sys = a.order != nullptr ? (long long)__ldg(a.order + idx) : first + idx;
-                    if (a.status[sys] == kActive) {
-                        r.status = kActive;
-                        r.load(a, sys);
+                    // every column of the link is requested before its status is looked at: the loads are the lane's own
+                    // (not coalesced) and a status test in front of them would put one more DRAM latency in series
+                    // (routed hour of 2.5 M links 5.91 -> 5.74 ms).  Claiming one link ahead and prefetching its columns
+                    // into L2 was tried on top: 6.60 ms — the second link index and 25 prefetches per link cost more
+                    // registers (628 B of spills) and issue slots than the shorter load latency returns.
+                    r.status = a.status[sys];
+                    r.load(a, sys);
+                    if (r.status == kActive) {
                         have = true;
                     } else {
                         if (a.cost != nullptr) a.cost[sys] = 0;
