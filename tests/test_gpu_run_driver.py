@@ -285,3 +285,28 @@ def test_driver_routed_two_ranks_equal_one_rank(tmp_path):
     assert np.array_equal(fin[order], one_f["outputs"][order_one])
     assert np.array_equal(den[order], one_d["outputs"][order_one])
     assert not list((tmp_path / "out").glob("nccl_id*"))  # the id file is gone once the communicator exists
+
+
+def test_driver_single_process_owning_several_contexts(tmp_path):
+    """--devices D0,D1: one process, one host thread and one device context per entry, thread r = rank r (the
+    reference's one MPI rank per GPU folded into one process).  Here both entries name GPU 0 — two contexts at once on
+    one device — and the files must equal those of two separate processes."""
+    write_case(tmp_path)
+    (tmp_path / "config.yaml").write_text(config_text("2021-01-01T00:00:00", "2021-01-02T00:00:00"))
+    run_driver(tmp_path, "config.yaml", world=2)
+    two = {r: (read_nc(tmp_path / "out" / f"final_rank_{r}.nc"), read_nc(tmp_path / "out" / f"dense_rank_{r}.nc")) for r in range(2)}
+    os.rename(tmp_path / "out", tmp_path / "out_two_processes")
+    os.makedirs(tmp_path / "out")
+    out = subprocess.run([RUN, str(tmp_path / "config.yaml"), "--devices", "0,0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for r in range(2):
+        f, d = read_nc(tmp_path / "out" / f"final_rank_{r}.nc"), read_nc(tmp_path / "out" / f"dense_rank_{r}.nc")
+        for a, b in ((f, two[r][0]), (d, two[r][1])):
+            assert a.keys() == b.keys()
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (r, k)
+    # a routed run cannot be folded this way: the ranks need their collective
+    cfg = config_text("2021-01-01T00:00:00", "2021-01-01T02:00:00").replace("uid: 204", "uid: 200") + 'routing:\n  enabled: true\n'
+    (tmp_path / "routed.yaml").write_text(cfg)
+    out = subprocess.run([RUN, str(tmp_path / "routed.yaml"), "--devices", "0,0"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "one process per GPU" in out.stderr

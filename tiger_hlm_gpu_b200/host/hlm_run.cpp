@@ -17,7 +17,11 @@
 // Routed runs (routing.enabled): links are dealt to ranks by sub-basin and the ranks all-gather the boundary
 // links' discharge once per coupling interval over NCCL (hlm_nccl.hpp; the id file goes to output.dir).
 //
-// usage: hlm_run CONFIG.yaml [--rank R] [--world W] [--device D] [--root DIR] [--quiet]
+// A single process can also own several GPUs (--devices 0,1,2,3): one host thread and one context per listed device,
+// thread r taking rank r of len(list) — the reference's one MPI rank per GPU (main.cpp:314-319) folded into one
+// process, for uncoupled models (a routed run needs the ranks' collective: one process per GPU).
+//
+// usage: hlm_run CONFIG.yaml [--rank R] [--world W] [--device D | --devices D0,D1,...] [--root DIR] [--quiet]
 #include <dirent.h>
 
 #include <chrono>
@@ -25,6 +29,7 @@
 #include <cstdlib>
 #include <future>
 #include <set>
+#include <thread>
 
 #include "hlm_config.hpp"
 #include "hlm_host.hpp"
@@ -40,6 +45,7 @@ struct Options {
     std::string config, root;
     int rank = 0, world = 1, device = -1;
     bool quiet = false;
+    std::vector<int> devices;  // --devices: one thread (rank) per entry
 };
 
 int env_int(const char* name, int dflt) {
@@ -459,6 +465,11 @@ int main(int argc, char** argv) {
             if (a == "--rank") opt.rank = std::stoi(next());
             else if (a == "--world") opt.world = std::stoi(next());
             else if (a == "--device") opt.device = std::stoi(next());
+            else if (a == "--devices") {
+                std::stringstream ss(next());
+                for (std::string tok; std::getline(ss, tok, ',');) opt.devices.push_back(std::stoi(tok));
+                if (opt.devices.empty()) throw std::runtime_error("--devices needs a comma-separated list of CUDA device ids");
+            }
             else if (a == "--root") opt.root = next();
             else if (a == "--quiet") opt.quiet = true;
             else if (!a.empty() && a[0] != '-' && opt.config.empty()) opt.config = a;
@@ -469,13 +480,39 @@ int main(int argc, char** argv) {
         }
     }
     if (opt.config.empty() || opt.world < 1 || opt.rank < 0 || opt.rank >= opt.world) {
-        std::fprintf(stderr, "usage: %s CONFIG.yaml [--rank R] [--world W] [--device D] [--root DIR] [--quiet]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s CONFIG.yaml [--rank R] [--world W] [--device D | --devices D0,D1,...] [--root DIR] [--quiet]\n", argv[0]);
         return 2;
     }
+    auto guarded = [](const Options& o) {
+        try {
+            return run(o);
+        } catch (const std::exception& e) {  // main.cpp prints and returns 1 on any failure
+            std::fprintf(stderr, "[rank %d] error: %s\n", o.rank, e.what());
+            return 1;
+        }
+    };
+    if (opt.devices.empty()) return guarded(opt);
+    // one process, several GPUs: thread r is rank r of devices.size() on device devices[r]
     try {
-        return run(opt);
-    } catch (const std::exception& e) {  // main.cpp prints and returns 1 on any failure
-        std::fprintf(stderr, "[rank %d] error: %s\n", opt.rank, e.what());
+        if (load_config(opt.config).routing.enabled && opt.devices.size() > 1)
+            throw std::runtime_error("routing with --devices: a routed run over several GPUs needs one process per GPU "
+                                     "(RANK / WORLD_SIZE / LOCAL_RANK), the ranks all-gather over NCCL");
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "hlm_run: %s\n", e.what());
         return 1;
     }
+    std::vector<int> rc(opt.devices.size(), 0);
+    std::vector<std::thread> threads;
+    for (size_t r = 0; r < opt.devices.size(); ++r) {
+        Options o = opt;
+        o.rank = (int)r;
+        o.world = (int)opt.devices.size();
+        o.device = opt.devices[r];
+        o.devices.clear();
+        threads.emplace_back([&rc, r, o, &guarded] { rc[r] = guarded(o); });
+    }
+    for (auto& t : threads) t.join();
+    for (int v : rc)
+        if (v) return v;
+    return 0;
 }
