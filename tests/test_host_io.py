@@ -512,3 +512,21 @@ def test_interval_boundaries_always_advance(io):
     assert io.hlmio_interval_boundaries(90.0, 200.0, b"1h", _p(out), 8) == 3 and list(out[:3]) == [120.0, 180.0, 200.0]
     assert io.hlmio_interval_boundaries(120.0, 240.0, b"1h", _p(out), 8) == 2 and list(out[:2]) == [180.0, 240.0]
     assert io.hlmio_interval_boundaries(0.0, 10.0, b"0", _p(out), 8) == -1
+
+
+def test_netcdf4_writer_edge_shapes(io, tmp_path):
+    """One link, one query, one state; duplicated states; a window longer than the series."""
+    for ns, nq, states, qw in ((1, 1, [3], 1), (1, 7, [2, 2, 0], 50), (9, 1, [0, 1, 2, 3, 4], 1)):
+        rng = np.random.default_rng(ns * 10 + nq)
+        dense = rng.standard_normal((ns, nq, 5))
+        t = 60.0 * np.arange(nq)
+        ids = np.arange(7, 7 + ns, dtype=np.int32)
+        st = np.array(states, np.int32)
+        p = str(tmp_path / f"e_{ns}_{nq}.nc")
+        rc = io.hlmio_write_dense_windows(p.encode(), _p(dense), _p(t), _p(ids), _p(st), len(st), nq, ns, 5, qw, NC4, 4, 0, 0)
+        assert rc == 0, io.hlmio_last_error().decode()
+        assert np.array_equal(read_var(io, p, "outputs"), dense[:, :, st])
+        assert np.array_equal(read_var(io, p, "system"), ids) and np.array_equal(read_var(io, p, "variable"), st)
+        pf = str(tmp_path / f"f_{ns}.nc")
+        io.hlmio_write_final_netcdf(pf.encode(), _p(np.ascontiguousarray(dense[:, 0])), _p(ids), _p(np.arange(5, dtype=np.int32)), ns, 5, NC4, 9)
+        assert np.array_equal(read_var(io, pf, "outputs"), dense[:, 0])
