@@ -228,10 +228,42 @@ __device__ __forceinline__ void dense_zero(const WindowArgs& a, long long sys, i
     dense_zero_rows(a.dense, a.dense_f32, a.dense_ncol, (sys - a.dense_sys0) * (long long)(a.q_hi - a.q_lo) + (q_from - a.q_lo), q_to - q_from);
 }
 
+// The seven stage slopes of a link.  Default: all in registers.  HLM_K_SHARED (experiment): the slopes of stages 2..5
+// in shared memory (one 8-byte column per thread and value, conflict-free), which takes 40 registers off a thread.
+template <typename T, int N> struct KStore {
+#ifdef HLM_K_SHARED
+    T reg[3][N];  // stages 0, 1, 6
+    T* sh;        // this thread's column of the CTA's array [4 * N][HLM_CTA_THREADS]
+    static __device__ __forceinline__ constexpr int slot(int s) { return s == 0 ? 0 : (s == 1 ? 1 : 2); }
+    __device__ __forceinline__ T get(int s, int i) const {
+        return (s >= 2 && s <= 5) ? sh[((s - 2) * N + i) * HLM_CTA_THREADS] : reg[slot(s)][i];
+    }
+    __device__ __forceinline__ void set(int s, int i, T v) {
+        if (s >= 2 && s <= 5) sh[((s - 2) * N + i) * HLM_CTA_THREADS] = v;
+        else reg[slot(s)][i] = v;
+    }
+    __device__ __forceinline__ void bind(T* base) { sh = base; }
+    __device__ __forceinline__ T* base() const { return sh; }
+#else
+    T reg[7][N];
+    __device__ __forceinline__ T get(int s, int i) const { return reg[s][i]; }
+    __device__ __forceinline__ void set(int s, int i, T v) { reg[s][i] = v; }
+    __device__ __forceinline__ void bind(T*) {}
+    __device__ __forceinline__ T* base() const { return nullptr; }
+#endif
+};
+#ifdef HLM_K_SHARED
+#define HLM_K_SHARED_DECL(T, N) __shared__ T hlm_ksh[4 * (N) * HLM_CTA_THREADS]
+#define HLM_K_SHARED_BASE (hlm_ksh + threadIdx.x)
+#else
+#define HLM_K_SHARED_DECL(T, N)
+#define HLM_K_SHARED_BASE nullptr
+#endif
+
 // One DOPRI5 attempt from (y, k0): fills k[1..6], y_next and the FSAL flag, returns err.
 // solver/rk45_step_dense.cuh:94-142.  All loops are compile-time unrolled; k stays in registers.
 template <class Model, typename T, bool kFast, typename G>
-__device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][Model::N_EQ], T h,
+__device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], KStore<T, Model::N_EQ>& k, T h,
                                            const T* F, const typename Model::template Link<T>& L, T rtol, T atol,
                                            T (&y_next)[Model::N_EQ], bool& fsal, G& bad) {
     using f = fp<T>;
@@ -247,10 +279,13 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
         for (int i = 0; i < N; ++i) {
             T acc = y[i];
 #pragma unroll
-            for (int j = 0; j < s; ++j) acc = f::fma(ha[j], k[j][i], acc);
+            for (int j = 0; j < s; ++j) acc = f::fma(ha[j], k.get(j, i), acc);
             yt[i] = acc;
         }
-        Model::template rhs<T, kFast>(yt, F, L, k[s], bad);
+        T ks[N];
+        Model::template rhs<T, kFast>(yt, F, L, ks, bad);
+#pragma unroll
+        for (int i = 0; i < N; ++i) k.set(s, i, ks[i]);
         if (s == 6) {
             // y_out = y + sum_{s<7} (h*b[s])*k[s].  a[6][j] == b[j] bit for bit for j < 6, so the first
             // six terms ARE the stage-6 state yt; only the last (zero-weight) term remains.  FSAL: k6 =
@@ -259,7 +294,7 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
             fsal = true;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                y_next[i] = f::fma(hb6, k[6][i], yt[i]);
+                y_next[i] = f::fma(hb6, ks[i], yt[i]);
                 fsal = fsal && f::same_bits(y_next[i], yt[i]);
             }
         }
@@ -272,7 +307,7 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], T (&k)[7][
     for (int i = 0; i < N; ++i) {
         T e = (T)0;
 #pragma unroll
-        for (int s = 0; s < 7; ++s) e = f::fma(he[s], k[s][i], e);
+        for (int s = 0; s < 7; ++s) e = f::fma(he[s], k.get(s, i), e);
         const T ymax = f::max_a(f::abs(y[i]), f::abs(y_next[i]));  // y NaN => y_next NaN: same result as fmax
         const T tol = f::fma(rtol, ymax, atol);
         const T ratio = f::abs(f::template div_err<kFast>(e, tol, bad));
@@ -291,14 +326,24 @@ template <class Model, typename T> struct ExactIO {
     T y[Model::N_EQ], k[7][Model::N_EQ], y_next[Model::N_EQ], F[2];
     T h, err, fac0;
     typename Model::template Link<T> L;
+    T* ksh;  // the lane's shared-memory column of stage slopes (HLM_K_SHARED), else unused
     bool fsal;
 };
 template <class Model, typename T>
 __device__ __noinline__ void exact_attempt(ExactIO<Model, T>& io, T rtol, T atol, T safety) {
     using f = fp<T>;
     bool unused = false, fsal = false;
+    constexpr int N = Model::N_EQ;
     Model::template rhs<T, false>(io.y, io.F, io.L, io.k[0], unused);  // rk45_kernel.cu:114
-    io.err = dopri_attempt<Model, T, false>(io.y, io.k, io.h, io.F, io.L, rtol, atol, io.y_next, fsal, unused);
+    KStore<T, N> k;
+    k.bind(io.ksh);
+#pragma unroll
+    for (int i = 0; i < N; ++i) k.set(0, i, io.k[0][i]);
+    io.err = dopri_attempt<Model, T, false>(io.y, k, io.h, io.F, io.L, rtol, atol, io.y_next, fsal, unused);
+#pragma unroll
+    for (int s = 1; s < 7; ++s)
+#pragma unroll
+        for (int i = 0; i < N; ++i) io.k[s][i] = k.get(s, i);
     io.fac0 = f::mul(safety, f::template pow_pos<false>(f::rcp(f::add(io.err, (T)1e-16)), (T)0.2, unused));
     io.fsal = fsal;
 }
@@ -323,6 +368,7 @@ template <class Model, typename T>
 __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
+    HLM_K_SHARED_DECL(T, N);
     const int lane = threadIdx.x & 31;
     const long long n_tiles = a.n_tiles;
     const bool run_to_end = (a.q_hi >= a.nq);
@@ -346,7 +392,9 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_windo
         }
 
         // ---- load lane state (coalesced columns) ----
-        T y[N], k[7][N], y_next[N];
+        T y[N], y_next[N];
+        KStore<T, N> k;
+        k.bind(HLM_K_SHARED_BASE);
 #pragma unroll
         for (int i = 0; i < N; ++i) y[i] = (T)a.y[(long long)i * a.ld + sys];
         T t = (T)a.t[sys], h = (T)a.h[sys];
@@ -421,7 +469,8 @@ template <class Model, typename T> struct LinkRun {
     using f = fp<T>;
     static constexpr int N = Model::N_EQ;
     long long sys, col;
-    T y[N], k[7][N], y_next[N];
+    T y[N], y_next[N];
+    KStore<T, N> k;
     T t, h, tq_next;
     int next_q, reject_run, status, budget;
     unsigned int n_acc, n_rej, n_jmp, n_at_load;
@@ -529,7 +578,9 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_lanes
     const long long last = ((a.tile_lo + a.n_tiles) << 5) < a.ns ? ((a.tile_lo + a.n_tiles) << 5) : a.ns;
     const long long n_links = last - first;
     const RunConsts<T> c(a);
+    HLM_K_SHARED_DECL(T, Model::N_EQ);
     LinkRun<Model, T> r;
+    r.k.bind(HLM_K_SHARED_BASE);
     bool have = false, exhausted = false;
     for (;;) {
         const unsigned int need = __ballot_sync(0xffffffffu, !have && !exhausted);
