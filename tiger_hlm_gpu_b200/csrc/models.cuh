@@ -38,6 +38,11 @@ struct Model204 {
     static constexpr int N_SP = 15;
     static constexpr int N_FORC = 2;
     static constexpr bool HAS_INFLOW = false;
+    // The surface store (state SURF) enters no other state's slope, and its own slope needs of the others only the
+    // store's net inflow d2 = x2 - x3: the step can run the hillslope (rhs_hill) ahead and the surface store's chain
+    // of pow()s (rhs_surf) beside it (dopri_attempt_split, rk45_window.cuh).  Same operations on the same operands.
+    static constexpr bool SPLIT_SURFACE = true;
+    static constexpr int SURF = 2;
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };  // R_* = fp<double>::div_recip of the divisor
 
@@ -141,6 +146,49 @@ struct Model204 {
             dydt[4] = f::sub(x4, (P.p[ALPHA4] >= (T)1) ? f::div(h_aq, P.p[ALPHA4]) : (T)0);
         }
     }
+
+    // ---- the same right-hand side in two parts (fast forms only), for dopri_attempt_split -------------------------
+    /// slopes of states 0, 1, 3, 4 (dydt[SURF] is not written; y[SURF] is not read) and the surface store's net
+    /// inflow d2 = x2 - x3.  Branch-free.
+    template <typename T, typename G>
+    static __device__ __forceinline__ void rhs_hill(const T* y, const T* F, const Link<T>& P, T* dydt, T& d2, G& bad) {
+        using f = fp<T>;
+        const T h_snow = y[0], h_stat = y[1], h_grav = y[3], h_aq = y[4];
+        const T rainfall = F[0], temperature = F[1];
+        const T snowmelt = (temperature >= P.p[TEMP_THR]) ? f::min_a(f::mul(temperature, P.p[MELT_F]), h_snow) : (T)0;
+        const T x1 = f::add(rainfall, snowmelt);
+        dydt[0] = f::sub(rainfall, snowmelt);
+        const T x2 = f::max0(f::sub(f::add(x1, h_stat), P.p[HU]));
+        const T d1 = f::sub(x1, x2);
+        const T Emax = f::min_a(f::mul((T)0.1, temperature), h_stat);
+        const T s = f::template div_by<true>(h_stat, P.p[HU], P.p[R_HU], bad);
+        dydt[1] = f::fma(-s, Emax, d1);
+        const T x3 = f::min_a(P.p[INFIL], x2);
+        d2 = f::sub(x2, x3);
+        const T x4 = f::min_a(P.p[PERCO], x3);
+        const T d3 = f::sub(x3, x4);
+        dydt[3] = f::sub(d3, f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad));
+        dydt[4] = f::sub(x4, f::template div_by<true>(h_aq, P.p[ALPHA4], P.p[R_ALPHA4], bad));
+    }
+    /// slope of the surface store.  kWet = false: the store is taken to be empty (slope = d2, exactly what rhs gives
+    /// for h_surf == +-0) and `not_dry` records a lane for which it is not.  kWet = true: branch-free — the pow chain
+    /// runs on a stand-in operand where the store is empty and the result is dropped there, so no flag is raised for it.
+    template <typename T, bool kWet, typename G>
+    static __device__ __forceinline__ T rhs_surf(T h_surf, T d2, const Link<T>& P, G& bad, bool& not_dry) {
+        using f = fp<T>;
+        if constexpr (!kWet) {
+            not_dry = not_dry || !(h_surf == (T)0);
+            return d2;
+        } else {
+            const bool empty = h_surf == (T)0;
+            const T x = empty ? (T)0.5 : h_surf;
+            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::template pow_pos<true>(x, (T)(2.0 / 3.0), bad)), P.wet_param(SQRT_SLOPE));
+            const T w = f::min_a((T)1, f::mul(f::template div_by<true>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
+                                                                     P.wet_param(R_A_H), bad), (T)60));
+            const T wet_slope = f::fma(-h_surf, w, d2);
+            return empty ? d2 : wet_slope;
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +211,8 @@ struct Model200 {
     static constexpr int N_SP = 15;
     static constexpr int N_FORC = 2;
     static constexpr bool HAS_INFLOW = true;
+    static constexpr bool SPLIT_SURFACE = false;  // the channel takes the surface store's outflow
+    static constexpr int SURF = 2;
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, CH, INVTAU,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };
 
@@ -280,6 +330,8 @@ struct DummyModel {
     static constexpr int N_SP = 0;
     static constexpr int N_FORC = 0;
     static constexpr bool HAS_INFLOW = false;
+    static constexpr bool SPLIT_SURFACE = false;
+    static constexpr int SURF = 0;
     static constexpr int kWetStride = 0;
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS&, double*) {}
     static __device__ __forceinline__ void prepare_wet(const double*, double*) {}

@@ -318,6 +318,90 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], KStore<T, 
     return max_ratio;
 }
 
+// The same attempt for a model whose surface store is a side chain (Model::SPLIT_SURFACE): the hillslope's slopes
+// (states != SURF: Model::rhs_hill, branch-free) of stage s+1 do not wait for the surface store's slope of stage s
+// (Model::rhs_surf: the pow), so the two are written side by side — hill(1); then surf(s) next to hill(s+1) for
+// s = 1..5; surf(6) — in straight-line code the instruction scheduler interleaves: the 63-deep pow chain of one stage
+// runs in the shadow of the next stage's sums.  Every value is computed by the operations of dopri_attempt on the
+// same operands (the fma chains keep their order), so the result is the same bits.
+// kWet = false: every stage's surface store is taken to be empty (no pow at all, no branch per stage); `not_dry`
+// comes back true for a lane where some stage's store was not, and the caller redoes the attempt with kWet = true.
+template <class Model, typename T, bool kWet, typename G>
+__device__ __forceinline__ T dopri_attempt_split(const T (&y)[Model::N_EQ], KStore<T, Model::N_EQ>& k, T h, const T* F,
+                                                 const typename Model::template Link<T>& L, T rtol, T atol,
+                                                 T (&y_next)[Model::N_EQ], bool& fsal, G& bad, bool& not_dry) {
+    using f = fp<T>;
+    constexpr int N = Model::N_EQ;
+    constexpr int S = Model::SURF;
+    const auto& TB = dp::tab<T>::get();
+    T ha[7][6];   // h * a[s][j]: stage s's coefficients serve hill(s) and, one step later, surf(s)
+    T d2[7];      // the surface store's net inflow at stage s
+    T yt6[N];     // the stage-6 state: y_next but for the zero-weight term
+#pragma unroll
+    for (int s = 1; s < 7; ++s) {
+        // ---- hill(s): states != S of stage s ----
+#pragma unroll
+        for (int j = 0; j < s; ++j) ha[s][j] = f::mul(h, TB.A[s][j]);
+        T yt[N], ks[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i == S) continue;
+            T acc = y[i];
+#pragma unroll
+            for (int j = 0; j < s; ++j) acc = f::fma(ha[s][j], k.get(j, i), acc);
+            yt[i] = acc;
+        }
+        yt[S] = (T)0;  // not read by rhs_hill
+        Model::template rhs_hill<T>(yt, F, L, ks, d2[s], bad);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i != S) k.set(s, i, ks[i]);
+        if (s == 6) {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i != S) yt6[i] = yt[i];
+        }
+        // ---- surf(s - 1) beside it (surf(6) after the loop) ----
+        if (s > 1) {
+            T acc = y[S];
+#pragma unroll
+            for (int j = 0; j < s - 1; ++j) acc = f::fma(ha[s - 1][j], k.get(j, S), acc);
+            k.set(s - 1, S, Model::template rhs_surf<T, kWet>(acc, d2[s - 1], L, bad, not_dry));
+        }
+    }
+    {
+        T acc = y[S];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc = f::fma(ha[6][j], k.get(j, S), acc);
+        yt6[S] = acc;
+        k.set(6, S, Model::template rhs_surf<T, kWet>(acc, d2[6], L, bad, not_dry));
+    }
+    // y_out and FSAL as in dopri_attempt
+    const T hb6 = f::mul(h, TB.B6);
+    fsal = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        y_next[i] = f::fma(hb6, k.get(6, i), yt6[i]);
+        fsal = fsal && f::same_bits(y_next[i], yt6[i]);
+    }
+    T he[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) he[s] = f::mul(h, TB.E[s]);
+    T max_ratio = (T)0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T e = (T)0;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) e = f::fma(he[s], k.get(s, i), e);
+        const T ymax = f::max_a(f::abs(y[i]), f::abs(y_next[i]));
+        const T tol = f::fma(rtol, ymax, atol);
+        const T ratio = f::abs(f::template div_err<true>(e, tol, bad));
+        if (i == 0) max_ratio = f::max0(ratio);
+        else if (ratio > max_ratio) max_ratio = ratio;
+    }
+    return max_ratio;
+}
+
 // The exact attempt (real div.rn / rcp.rn / libdevice pow), for the rare attempt whose operands leave the domain
 // of the fast forms.  Out of line on copies of the lane's state in local memory: the hot loop then holds one
 // attempt, not two, which halves its instruction footprint (the L1.5 instruction cache is 32 KB, the two bodies
