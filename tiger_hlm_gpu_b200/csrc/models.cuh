@@ -43,6 +43,10 @@ struct Model204 {
     // of pow()s (rhs_surf) beside it (dopri_attempt_split, rk45_window.cuh).  Same operations on the same operands.
     static constexpr bool SPLIT_SURFACE = true;
     static constexpr int SURF = 2;
+    static constexpr int N_SIDE = 1;    // states of the side chain, in the order rhs_side takes and returns them
+    static constexpr int HILL_OUT = 1;  // values rhs_hill hands to rhs_side: d2
+    static __host__ __device__ constexpr int side_state(int k) { return k == 0 ? SURF : -1; }
+    static __host__ __device__ constexpr bool is_side(int i) { return i == SURF; }
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, MELT_F, TEMP_THR,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };  // R_* = fp<double>::div_recip of the divisor
 
@@ -148,10 +152,10 @@ struct Model204 {
     }
 
     // ---- the same right-hand side in two parts (fast forms only), for dopri_attempt_split -------------------------
-    /// slopes of states 0, 1, 3, 4 (dydt[SURF] is not written; y[SURF] is not read) and the surface store's net
-    /// inflow d2 = x2 - x3.  Branch-free.
+    /// slopes of states 0, 1, 3, 4 (dydt[SURF] is not written; y[SURF] is not read) and, in ho[0], the surface store's
+    /// net inflow d2 = x2 - x3.  Branch-free.
     template <typename T, typename G>
-    static __device__ __forceinline__ void rhs_hill(const T* y, const T* F, const Link<T>& P, T* dydt, T& d2, G& bad) {
+    static __device__ __forceinline__ void rhs_hill(const T* y, const T* F, const Link<T>& P, T* dydt, T (&ho)[HILL_OUT], G& bad) {
         using f = fp<T>;
         const T h_snow = y[0], h_stat = y[1], h_grav = y[3], h_aq = y[4];
         const T rainfall = F[0], temperature = F[1];
@@ -164,7 +168,7 @@ struct Model204 {
         const T s = f::template div_by<true>(h_stat, P.p[HU], P.p[R_HU], bad);
         dydt[1] = f::fma(-s, Emax, d1);
         const T x3 = f::min_a(P.p[INFIL], x2);
-        d2 = f::sub(x2, x3);
+        ho[0] = f::sub(x2, x3);
         const T x4 = f::min_a(P.p[PERCO], x3);
         const T d3 = f::sub(x3, x4);
         dydt[3] = f::sub(d3, f::template div_by<true>(h_grav, P.p[ALPHA3], P.p[R_ALPHA3], bad));
@@ -174,11 +178,13 @@ struct Model204 {
     /// for h_surf == +-0) and `not_dry` records a lane for which it is not.  kWet = true: branch-free — the pow chain
     /// runs on a stand-in operand where the store is empty and the result is dropped there, so no flag is raised for it.
     template <typename T, bool kWet, typename G>
-    static __device__ __forceinline__ T rhs_surf(T h_surf, T d2, const Link<T>& P, G& bad, bool& not_dry) {
+    static __device__ __forceinline__ void rhs_side(const T (&ys)[N_SIDE], const T (&ho)[HILL_OUT], const Link<T>& P, T (&ks)[N_SIDE],
+                                                    G& bad, bool& not_dry) {
         using f = fp<T>;
+        const T h_surf = ys[0], d2 = ho[0];
         if constexpr (!kWet) {
             not_dry = not_dry || !(h_surf == (T)0);
-            return d2;
+            ks[0] = d2;
         } else {
             const bool empty = h_surf == (T)0;
             const T x = empty ? (T)0.5 : h_surf;
@@ -186,7 +192,7 @@ struct Model204 {
             const T w = f::min_a((T)1, f::mul(f::template div_by<true>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
                                                                      P.wet_param(R_A_H), bad), (T)60));
             const T wet_slope = f::fma(-h_surf, w, d2);
-            return empty ? d2 : wet_slope;
+            ks[0] = empty ? d2 : wet_slope;
         }
     }
 };
@@ -211,8 +217,13 @@ struct Model200 {
     static constexpr int N_SP = 15;
     static constexpr int N_FORC = 2;
     static constexpr bool HAS_INFLOW = true;
-    static constexpr bool SPLIT_SURFACE = false;  // the channel takes the surface store's outflow
+    // Not split (dopri_attempt_split): the surface store and, behind it, the channel do hang off the hillslope as a side
+    // chain, and the split attempt gives the same bits, but with two pow chains beside the hillslope's sums the lane
+    // kernel spills 1.3 KB per thread: routed hour 5.72 -> 6.07 ms.  Measured, not kept.
+    static constexpr bool SPLIT_SURFACE = false;
     static constexpr int SURF = 2;
+    static constexpr int N_SIDE = 0;
+    static constexpr int HILL_OUT = 0;
     enum { INFIL, PERCO, HU, INV_N, SQRT_SLOPE, LEN, A_H, ALPHA3, ALPHA4, CH, INVTAU,
            R_HU, R_A_H, R_ALPHA3, R_ALPHA4 };
 
@@ -332,6 +343,8 @@ struct DummyModel {
     static constexpr bool HAS_INFLOW = false;
     static constexpr bool SPLIT_SURFACE = false;
     static constexpr int SURF = 0;
+    static constexpr int N_SIDE = 0;
+    static constexpr int HILL_OUT = 0;
     static constexpr int kWetStride = 0;
     static __device__ __forceinline__ void prepare(const SpatialParamsAoS&, double*) {}
     static __device__ __forceinline__ void prepare_wet(const double*, double*) {}

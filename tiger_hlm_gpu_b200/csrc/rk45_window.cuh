@@ -32,6 +32,12 @@
 #ifndef HLM_BLOCKS_PER_SM
 #define HLM_BLOCKS_PER_SM 3
 #endif
+// FP32 instances of the tile kernel: 4 CTAs/SM (128 registers, 4 bytes of spills).  Measured at 1 M links, dry / wet:
+// 3 CTAs 12.09 / 16.25 ms, 4 CTAs 11.33 / 14.77, 5 CTAs (96 registers, 264 B of spills) 11.34 / 15.60, 6 CTAs 11.98 / 16.03
+// (profiles/r2t_ab_fp32_occupancy.log).  The FP64 instances stay at 3: their fourth CTA does not fit without spills.
+#ifndef HLM_BLOCKS_PER_SM_F32
+#define HLM_BLOCKS_PER_SM_F32 4
+#endif
 #ifndef HLM_CTA_THREADS
 #define HLM_CTA_THREADS 128  // the kernels only use the lane id: any multiple of 32 works
 #endif
@@ -318,13 +324,14 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], KStore<T, 
     return max_ratio;
 }
 
-// The same attempt for a model whose surface store is a side chain (Model::SPLIT_SURFACE): the hillslope's slopes
-// (states != SURF: Model::rhs_hill, branch-free) of stage s+1 do not wait for the surface store's slope of stage s
-// (Model::rhs_surf: the pow), so the two are written side by side — hill(1); then surf(s) next to hill(s+1) for
-// s = 1..5; surf(6) — in straight-line code the instruction scheduler interleaves: the 63-deep pow chain of one stage
-// runs in the shadow of the next stage's sums.  Every value is computed by the operations of dopri_attempt on the
-// same operands (the fma chains keep their order), so the result is the same bits.
-// kWet = false: every stage's surface store is taken to be empty (no pow at all, no branch per stage); `not_dry`
+// The same attempt for a model whose rhs has a side chain (Model::SPLIT_SURFACE): states nothing on the hillslope
+// depends on — Model204's surface store; Model 200's surface store and, behind it, its channel.  The hillslope's slopes
+// (Model::rhs_hill, branch-free) of stage s+1 do not wait for the side chain's slopes of stage s (Model::rhs_side: the
+// pows), so the two are written side by side — hill(1); then side(s) next to hill(s+1) for s = 1..5; side(6) — in
+// straight-line code the instruction scheduler interleaves: the 63-deep pow chain of one stage runs in the shadow of
+// the next stage's sums.  Every value is computed by the operations of dopri_attempt on the same operands (the fma
+// chains keep their order), so the result is the same bits.
+// kWet = false: every stage's surface store is taken to be empty (no surface pow, no branch per stage); `not_dry`
 // comes back true for a lane where some stage's store was not, and the caller redoes the attempt with kWet = true.
 template <class Model, typename T, bool kWet, typename G>
 __device__ __forceinline__ T dopri_attempt_split(const T (&y)[Model::N_EQ], KStore<T, Model::N_EQ>& k, T h, const T* F,
@@ -332,50 +339,53 @@ __device__ __forceinline__ T dopri_attempt_split(const T (&y)[Model::N_EQ], KSto
                                                  T (&y_next)[Model::N_EQ], bool& fsal, G& bad, bool& not_dry) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
-    constexpr int S = Model::SURF;
+    constexpr int NS = Model::N_SIDE, NH = Model::HILL_OUT;
     const auto& TB = dp::tab<T>::get();
-    T ha[7][6];   // h * a[s][j]: stage s's coefficients serve hill(s) and, one step later, surf(s)
-    T d2[7];      // the surface store's net inflow at stage s
-    T yt6[N];     // the stage-6 state: y_next but for the zero-weight term
+    T ha[7][6];      // h * a[s][j]: stage s's coefficients serve hill(s) and, one step later, side(s)
+    T ho[7][NH];     // what the hillslope of stage s hands to the side chain
+    T yt6[N];        // the stage-6 state: y_next but for the zero-weight term
+    auto side = [&](int s) {  // states of the side chain at stage s -> their slopes
+        T ys[NS], ks[NS];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) {
+            const int i = Model::side_state(c);
+            T acc = y[i];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (j < s) acc = f::fma(ha[s][j], k.get(j, i), acc);
+            ys[c] = acc;
+            if (s == 6) yt6[i] = acc;
+        }
+        Model::template rhs_side<T, kWet>(ys, ho[s], L, ks, bad, not_dry);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) k.set(s, Model::side_state(c), ks[c]);
+    };
 #pragma unroll
     for (int s = 1; s < 7; ++s) {
-        // ---- hill(s): states != S of stage s ----
+        // ---- hill(s): the states off the side chain ----
 #pragma unroll
         for (int j = 0; j < s; ++j) ha[s][j] = f::mul(h, TB.A[s][j]);
         T yt[N], ks[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            if (i == S) continue;
+            if (Model::is_side(i)) {
+                yt[i] = (T)0;  // not read by rhs_hill
+                continue;
+            }
             T acc = y[i];
 #pragma unroll
             for (int j = 0; j < s; ++j) acc = f::fma(ha[s][j], k.get(j, i), acc);
             yt[i] = acc;
+            if (s == 6) yt6[i] = acc;
         }
-        yt[S] = (T)0;  // not read by rhs_hill
-        Model::template rhs_hill<T>(yt, F, L, ks, d2[s], bad);
+        Model::template rhs_hill<T>(yt, F, L, ks, ho[s], bad);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (i != S) k.set(s, i, ks[i]);
-        if (s == 6) {
-#pragma unroll
-            for (int i = 0; i < N; ++i)
-                if (i != S) yt6[i] = yt[i];
-        }
-        // ---- surf(s - 1) beside it (surf(6) after the loop) ----
-        if (s > 1) {
-            T acc = y[S];
-#pragma unroll
-            for (int j = 0; j < s - 1; ++j) acc = f::fma(ha[s - 1][j], k.get(j, S), acc);
-            k.set(s - 1, S, Model::template rhs_surf<T, kWet>(acc, d2[s - 1], L, bad, not_dry));
-        }
+            if (!Model::is_side(i)) k.set(s, i, ks[i]);
+        // ---- side(s - 1) beside it (side(6) after the loop) ----
+        if (s > 1) side(s - 1);
     }
-    {
-        T acc = y[S];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc = f::fma(ha[6][j], k.get(j, S), acc);
-        yt6[S] = acc;
-        k.set(6, S, Model::template rhs_surf<T, kWet>(acc, d2[6], L, bad, not_dry));
-    }
+    side(6);
     // y_out and FSAL as in dopri_attempt
     const T hb6 = f::mul(h, TB.B6);
     fsal = true;
@@ -449,7 +459,7 @@ __device__ __forceinline__ long long forcing_index(double t, double dt_min, long
 // when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
 // threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
 template <class Model, typename T>
-__global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
+__global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_PER_SM_F32 : HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
     HLM_K_SHARED_DECL(T, N);
