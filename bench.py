@@ -41,8 +41,8 @@ if ROOT not in sys.path:
 
 # STATIC figures from a committed ncu capture, not measured live (ncu counters are not available inside a timed run):
 # re-derive them with tools/ncu_summary.py whenever the window kernel changes.  PROFILE names the capture.
-PROFILE = {"file": "profiles/r2g_ncu_full_window_kernel_10M.csv", "commit": "b2298e4", "dram_bytes_per_link_per_launch": 1419.6,
-           "fp64_pipe_utilization": 0.627}
+PROFILE = {"file": "profiles/r2s_ncu_full_window_kernel_10M.csv", "commit": "62666ca", "dram_bytes_per_link_per_launch": 1408.4,
+           "fp64_pipe_utilization": 0.663}
 DRAM_BYTES_PER_LINK_PER_LAUNCH = PROFILE["dram_bytes_per_link_per_launch"]
 W_MIN_FLOP_PER_ATTEMPT = 561.0  # minimal-algorithm nominal FP64 flop per attempted Model204 step
 PRM6 = [1e-6, 1e-6, 1e-9, 0.9, 0.2, 10.0]  # initialStep (main.cpp:633-640), rtol, atol, safety, min/maxScale
