@@ -293,7 +293,8 @@ int hlm_measure_fma_peak(hlm_ctx* ctx, int bits, double* tflops);
 
 /* Element-wise probe of the device's arithmetic on host arrays x, y -> out (n elements):
  * op 0 = libdevice pow(x, y); 1 = rcp.approx.ftz.f64(x) (the MUFU.RCP64H seed pow starts from);
- * 2 = x / y (div.rn.f64); 3 = sqrt.rn.f64(x); 4 = the kernels' inlined pow (fp_exact.cuh pow_pos).
+ * 2 = x / y (div.rn.f64); 3 = sqrt.rn.f64(x); 4 = the kernels' inlined pow (fp_exact.cuh pow_pos);
+ * 5 = Model 200's x^(1/5), 6 = its x^(2/3) (fp_exact.cuh root5 / cbrt2; y unused).
  * Lets tests compare device and host arithmetic. */
 int hlm_debug_eval(hlm_ctx* ctx, int op, const double* x, const double* y, double* out, long long n);
 

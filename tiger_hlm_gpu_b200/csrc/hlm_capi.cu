@@ -341,6 +341,8 @@ __global__ void probe_kernel(int op, const double* __restrict__ x, const double*
         if (g.failed()) r = hlm::fp<double>::pow_pos<false>(x[i], y[i], g);
         break;
     }
+    case 5: r = hlm::fp<double>::root5(x[i]); break;  // Model 200's x^(1/5)
+    case 6: r = hlm::fp<double>::cbrt2(x[i]); break;  // Model 200's x^(2/3)
     default: r = 0.0;
     }
     out[i] = r;
@@ -1464,7 +1466,7 @@ int hlm_route_peer_close(hlm_ctx* c) {
 }
 
 int hlm_debug_eval(hlm_ctx* c, int op, const double* x, const double* y, double* out, long long n) {
-    HLM_REQUIRE(c && x && y && out && n > 0 && op >= 0 && op <= 4, "hlm_debug_eval: bad argument");
+    HLM_REQUIRE(c && x && y && out && n > 0 && op >= 0 && op <= 6, "hlm_debug_eval: bad argument");
     if (int r = use_device(c)) return r;
     double *dx = nullptr, *dy = nullptr, *dout = nullptr;
     HLM_CUDA(cudaMalloc(&dx, sizeof(double) * n));

@@ -217,12 +217,16 @@ struct Model204 {
 // snow store (same expressions, same two contractions) draining into the link's channel with the
 // Hillslope-Link Model's nonlinear-celerity routing equation (Mantilla & Gupta 2005; the form the
 // Iowa HLM uses):
-//     dq/dt = invtau * q_e^0.2 * ((runoff*CH + q_in) - q),   q_e = max(q, 1e-6 m3/s)
+//     dq/dt = invtau * q_e^(1/5) * ((runoff*CH + q_in) - q),   q_e = max(q, 1e-6 m3/s)
 //     runoff = (h_surf*w + out_grav) + out_aq   [m/min],  CH = A_h * 1e6/60  [km2 * m/min -> m3/s]
 //     invtau = 19.8 / ((800 * L) * sqrt(A_h^0.2))   [1/min]   (v_r 0.33 m/s, lambda1 0.2, lambda2 -0.1)
 // q_in is the discharge entering from upstream links (0 for an unrouted run); it is constant over an
-// interval, set per link through WindowArgs::qin (routing, rk45_window.cuh).  The CPU restatement the
-// tests compare with lives with the test infrastructure; the independent pin is SciPy (tests).
+// interval, set per link through WindowArgs::qin (routing, rk45_window.cuh).  Being project-defined, its two power
+// laws — q_e^(1/5) and the surface store's h^(2/3) — are evaluated by fp<T>::root5 / cbrt2 (fp_exact.cuh: a bit-trick
+// seed and Newton steps, within 3 ulp, a quarter of libdevice pow's instructions) rather than by pow(): with six right-hand
+// sides per attempt the channel's pow alone was a third of the lane kernel's instructions.  Model204, whose arithmetic
+// the reference defines, keeps pow().  The CPU restatement the tests compare with lives with the test infrastructure;
+// the independent pin is SciPy (tests).
 // ---------------------------------------------------------------------------------------------
 struct Model200 {
     static constexpr int UID = 200;
@@ -326,7 +330,7 @@ struct Model200 {
             dydt[2] = d2;
             out_surf = (T)0;
         } else {
-            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::template pow_pos<kFast>(h_surf, (T)(2.0 / 3.0), bad)), P.wet_param(SQRT_SLOPE));
+            const T alfa2 = f::mul(f::mul(P.wet_param(INV_N), f::cbrt2(h_surf)), P.wet_param(SQRT_SLOPE));
             const T w = f::min_a((T)1, f::mul(f::template div_by<kFast>(f::mul(alfa2, P.wet_param(LEN)), P.wet_param(A_H),
                                                                       P.wet_param(R_A_H), bad), (T)60));
             dydt[2] = f::fma(-h_surf, w, d2);
@@ -351,7 +355,7 @@ struct Model200 {
         const T runoff = f::add(f::add(out_surf, out_grav), out_aq);
         const T lateral = f::mul(runoff, P.p[CH]);
         const T qe = f::max_a((T)1e-6, q);
-        const T cel = f::template pow_pos<kFast>(qe, (T)0.2, bad);
+        const T cel = f::root5(qe);
         dydt[0] = f::mul(f::mul(P.p[INVTAU], cel), f::sub(f::add(lateral, P.qin), q));
     }
 };
