@@ -322,7 +322,7 @@ __device__ __forceinline__ T dopri_attempt(const T (&y)[Model::N_EQ], KStore<T, 
         const T ratio = f::abs(f::template div_err<kFast>(e, tol, bad));
         // NaN-ignoring form of the reference: if (ratio > max_ratio) max_ratio = ratio, from 0
         if (i == 0) max_ratio = f::max0(ratio);
-        else if (ratio > max_ratio) max_ratio = ratio;
+        else max_ratio = f::max_a(max_ratio, ratio);  // (ratio > max_ratio) ? ratio : max_ratio
     }
     return max_ratio;
 }
@@ -410,7 +410,7 @@ __device__ __forceinline__ T dopri_attempt_split(const T (&y)[Model::N_EQ], KSto
         const T tol = f::fma(rtol, ymax, atol);
         const T ratio = f::abs(f::template div_err<true>(e, tol, bad));
         if (i == 0) max_ratio = f::max0(ratio);
-        else if (ratio > max_ratio) max_ratio = ratio;
+        else max_ratio = f::max_a(max_ratio, ratio);  // (ratio > max_ratio) ? ratio : max_ratio
     }
     return max_ratio;
 }
