@@ -64,7 +64,7 @@ def parse_args():
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                     help="routed: boundary discharge all-gathered over NCCL, or stored into every rank's halo vector by the "
                          "kernels themselves (CUDA IPC peer memory) with a one-element all-reduce as the barrier")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes"],
+    ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes", "sorted"],
                     help="how links are dealt to lanes (hlm_set_schedule); auto = lanes for routed runs, tiles otherwise")
     ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
     ap.add_argument("--wet-fraction", type=float, default=0.0,

@@ -145,6 +145,9 @@ int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
 #define HLM_SCHEDULE_AUTO 0
 #define HLM_SCHEDULE_TILES 1
 #define HLM_SCHEDULE_LANES 2
+/* SORTED_TILES (models with an inflow term, i.e. Model 200; TILES otherwise): tiles of 32 links that took the SAME
+ * number of attempts in the previous launch, whatever their indices — lockstep tiles where neighbouring links differ. */
+#define HLM_SCHEDULE_SORTED_TILES 3
 int hlm_set_schedule(hlm_ctx* ctx, int mode);
 /* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */
 int hlm_set_precision(hlm_ctx* ctx, int bits);

@@ -82,7 +82,10 @@ def routed_inputs(ns, subbasin, seed=4):
     return sp, col, pr, t2m, y0
 
 
-def test_routed_single_rank_equals_oracle_bit_for_bit(solver):
+@pytest.mark.parametrize("schedule", ["auto", "sorted", "tiles"])
+def test_routed_single_rank_equals_oracle_bit_for_bit(solver, schedule):
+    """Every way of dealing links to lanes (auto = lane refill; sorted = tiles of links with equal attempt counts in the
+    previous interval; tiles = 32 consecutive links) integrates each link with the same arithmetic: same bits."""
     ns, tf, dt, qpi = 3000, 360.0, 15.0, 2
     sp, col, pr, t2m, y0 = routed_inputs(ns, 256)
     p1 = routing.plan(sp["stream"], sp["next_stream"], 1, subbasin_links=256)
@@ -93,6 +96,7 @@ def test_routed_single_rank_equals_oracle_bit_for_bit(solver):
     edges = np.arange(0.0, tf + 1e-9, dt)
     dense_g = np.zeros_like(dense_o)
     try:
+        solver.set_schedule(schedule)
         rs = routing.RoutedSolver(solver, 200, p1.ranks[0], 1, 0)
         for i, (a, b) in enumerate(zip(edges[:-1], edges[1:])):
             tq = a + (b - a) * np.arange(1, qpi + 1) / qpi
@@ -105,6 +109,7 @@ def test_routed_single_rank_equals_oracle_bit_for_bit(solver):
         qin, _ = solver.route_peek()
         r = rs.end()
     finally:
+        solver.set_schedule("auto")
         solver.set_stream(None)
         solver.set_stiff_fallback(False)
         solver.route_clear()

@@ -258,8 +258,8 @@ class Solver:
         return out
 
     def set_schedule(self, mode: str = "auto"):
-        """'tiles', 'lanes' or 'auto' (lanes for routed runs) — hlm_set_schedule."""
-        _check(self._lib.hlm_set_schedule(self._h, {"auto": 0, "tiles": 1, "lanes": 2}[mode]))
+        """'tiles', 'lanes', 'sorted' (tiles of links with equal attempt counts; Model 200) or 'auto' — hlm_set_schedule."""
+        _check(self._lib.hlm_set_schedule(self._h, {"auto": 0, "tiles": 1, "lanes": 2, "sorted": 3}[mode]))
 
     def set_precision(self, bits: int):
         _check(self._lib.hlm_set_precision(self._h, bits))

@@ -427,20 +427,29 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     else if (c->uid == hlm::Model200::UID) { launch = f32 ? hlm::launch_rk45_200_f32 : hlm::launch_rk45_200_f64; divergent_model = true; }
     else if (c->uid == hlm::DummyModel::UID) launch = f32 ? hlm::launch_rk45_dummy_f32 : hlm::launch_rk45_dummy_f64;
     else return fail(HLM_ERR_INVALID, "unknown model uid");
-    const bool lanes = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && (c->routed || divergent_model));
+    // Which schedule.  Where links take unlike numbers of attempts per launch (Model 200, every routed run) AUTO asks
+    // for sorted tiles — tiles of 32 links that took the same number of attempts in the previous launch — when the model's
+    // kernel can follow an order (the ones with an inflow term) and there is one (from the second launch over all links
+    // on); a launch without an order goes to lane refill, which also records the counts the next launch is sorted by.
+    const bool has_inflow = c->uid == hlm::Model200::UID;
+    const bool divergent = c->routed || divergent_model;
+    const bool lanes_asked = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && divergent);
+    const bool sorted_tiles = has_inflow && !f32 && (c->schedule == HLM_SCHEDULE_SORTED_TILES || (c->schedule == HLM_SCHEDULE_AUTO && divergent));
     hlm::WindowArgs a = a_in;
     // Longest first.  Under lane refill a launch ends with the lanes that drew a long link late while the others have
     // run out of links (22 of 32 threads active on the routed workload).  A link's attempt count changes slowly from
     // one launch to the next, so the launch deals the links in the order of the attempts they took last time, most
     // first.  One stable 4-bit radix pass (attempts / 4, up to 60): links with like counts keep their ascending order,
     // so neighbouring lanes still touch neighbouring memory.  Only for launches over all links of the session.
-    if (lanes && c->longest_first && !f32 && a.tile_lo == 0 && a.n_tiles == (c->ns + 31) / 32 && c->ns < (1LL << 31)) {
+    // Sorted tiles use the same order, sorted by the whole count (6 bits): a tile is 32 links of EQUAL predicted count.
+    if ((lanes_asked || sorted_tiles) && c->longest_first && !f32 && a.tile_lo == 0 && a.n_tiles == (c->ns + 31) / 32 && c->ns < (1LL << 31)) {
+        const int key_lo = sorted_tiles ? 0 : 2;
         const size_t n = (size_t)c->ns;
         HLM_CUDA(c->cost.reserve((size_t)c->ld));
         // In routed runs the order is renewed every fourth launch: the sort is 46 us of a 1.1 ms coupling interval, and an
         // order a few intervals old deals the links nearly as well (any permutation is a valid order; routed hour 4.60 ->
         // 4.52 ms).  Unrouted launches are long (a day of Model 200: 5 ms) and their counts move more: every launch.
-        if (c->cost_ns == c->ns && (c->order_ns != c->ns || c->order_age >= (c->routed ? 4 : 1))) {
+        if (c->cost_ns == c->ns && (c->order_ns != c->ns || c->order_age >= ((c->routed && !sorted_tiles) ? 4 : 1))) {
             HLM_CUDA(c->cost_sorted.reserve(n));
             HLM_CUDA(c->order.reserve(n));
             if (c->iota.cap < n) {
@@ -451,10 +460,10 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
             }
             size_t tmp_bytes = 0;
             HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
-                                                               (int)n, 2, 6, c->stream));
+                                                               (int)n, key_lo, 6, c->stream));
             HLM_CUDA(c->sort_tmp.reserve(tmp_bytes));
             HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->sort_tmp.p, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
-                                                               (int)n, 2, 6, c->stream));
+                                                               (int)n, key_lo, 6, c->stream));
             c->launches += 3;  // histogram, scan, one scatter pass
             c->order_ns = c->ns;
             c->order_age = 0;
@@ -478,6 +487,7 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     HLM_CUDA(cudaEventRecord(e0, c->stream));
     // routed runs take a few attempts per link per launch: the lane kernel that tests for "finished" right
     // after the attempt (rk45_window.cuh, kEarlyLeave)
+    const bool lanes = (lanes_asked || sorted_tiles) && !(sorted_tiles && a.order != nullptr);
     HLM_CUDA(launch(lanes ? (c->routed ? 2 : 1) : 0, a, c->sm_count, c->stream));
     HLM_CUDA(cudaEventRecord(e1, c->stream));
     c->timing.emplace_back(e0, e1);
@@ -711,8 +721,8 @@ int hlm_set_stiff_fallback(hlm_ctx* c, int enable) {
 }
 
 int hlm_set_schedule(hlm_ctx* c, int mode) {
-    HLM_REQUIRE(c && (mode == HLM_SCHEDULE_AUTO || mode == HLM_SCHEDULE_TILES || mode == HLM_SCHEDULE_LANES),
-                "hlm_set_schedule: mode must be HLM_SCHEDULE_AUTO, _TILES or _LANES");
+    HLM_REQUIRE(c && (mode == HLM_SCHEDULE_AUTO || mode == HLM_SCHEDULE_TILES || mode == HLM_SCHEDULE_LANES || mode == HLM_SCHEDULE_SORTED_TILES),
+                "hlm_set_schedule: mode must be HLM_SCHEDULE_AUTO, _TILES, _LANES or _SORTED_TILES");
     c->schedule = mode;
     return HLM_OK;
 }

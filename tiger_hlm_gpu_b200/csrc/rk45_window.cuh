@@ -458,6 +458,15 @@ __device__ __forceinline__ long long forcing_index(double t, double dt_min, long
     return idx;
 }
 
+// A link's sort key for the next launch: the attempts it took in this one in 6 bits — exact up to 15, then in steps of
+// 2 (to 47), 4 (to 111) and 16 (saturating at 368) — so that links of equal key take nearly equal numbers of attempts
+// both where counts are small (a routed interval: 1 to 20) and where they are large (a day of Model 200: 10 to 300).
+__device__ __forceinline__ int cost_key(unsigned int attempts) {
+    const unsigned int a = attempts;
+    const unsigned int k = a < 16u ? a : (a < 48u ? 16u + ((a - 16u) >> 1) : (a < 112u ? 32u + ((a - 48u) >> 2) : 48u + ((a - 112u) >> 4)));
+    return (int)(k < 63u ? k : 63u);
+}
+
 // Tile schedule: a warp takes 32 consecutive links and stays with them until the slowest lane leaves.  Right
 // when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
 // threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
@@ -480,8 +489,14 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         if (lane == 0) tile = atomicAdd(a.tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if ((long long)tile >= n_tiles) break;
-        const long long sys = ((a.tile_lo + (long long)tile) << 5) + lane;
+        long long sys = ((a.tile_lo + (long long)tile) << 5) + lane;
         if (sys >= a.ns) continue;
+        // Sorted tiles (models with an inflow term, i.e. the ones routed runs use): the tile is 32 consecutive entries of
+        // the launch's order — links that took the same number of attempts in the previous launch — instead of 32
+        // consecutive links, so its lanes finish together although neighbouring links do not.
+        if constexpr (Model::HAS_INFLOW) {
+            if (a.order != nullptr) sys = (long long)__ldg(a.order + (sys - (a.tile_lo << 5)));
+        }
         int status = a.status[sys];
         if (status != kActive) {  // finished, abandoned or in the fallback's hands: no record from this path
             dense_zero(a, sys, a.q_lo, a.q_hi);
@@ -498,6 +513,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         int next_q = a.next_q[sys];
         int reject_run = a.reject_run[sys];
         unsigned int n_acc = a.n_accept[sys], n_rej = a.n_reject[sys], n_jmp = a.n_jump[sys];
+        [[maybe_unused]] const unsigned int n_at_load = n_acc + n_rej + n_jmp;
         typename Model::template Link<T> L;
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
@@ -535,6 +551,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
+            if (a.cost != nullptr) a.cost[sys] = cost_key(n_acc + n_rej + n_jmp - n_at_load);  // the next launch's sort key
             if (status != kActive) route_publish(a, sys, (double)y[0]);
         }
     }
@@ -727,7 +744,7 @@ template <class Model, typename T> struct LinkRun {
         a.n_accept[sys] = n_acc;
         a.n_reject[sys] = n_rej;
         a.n_jump[sys] = n_jmp;
-        if (a.cost != nullptr) a.cost[sys] = (int)min(n_acc + n_rej + n_jmp - n_at_load, 63u);  // the sort reads 6 bits
+        if (a.cost != nullptr) a.cost[sys] = cost_key(n_acc + n_rej + n_jmp - n_at_load);  // the sort reads 6 bits
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
