@@ -444,12 +444,37 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     // Sorted tiles use the same order, sorted by the whole count (6 bits): a tile is 32 links of EQUAL predicted count.
     if ((lanes_asked || sorted_tiles) && c->longest_first && !f32 && a.tile_lo == 0 && a.n_tiles == (c->ns + 31) / 32 && c->ns < (1LL << 31)) {
         const int key_lo = sorted_tiles ? 0 : 2;
+        // Sorted tiles, block by block.  A tile's 32 links are then 32 different places of every column, and sorted over
+        // all links the rest of each 32-byte sector they touch belongs to links of other counts, which other tiles
+        // reach much later: 1.3 KB of DRAM reads per link instead of 0.3 (ncu, routed interval of 2.5 M links).  So the
+        // order is by attempts INSIDE blocks of 32 768 consecutive links (10 MB of state and parameters: L2-resident
+        // while the launch works through the block) and by block before that: routed interval 0.965 -> 0.817 ms.  Only
+        // for routed runs: an unrouted launch is a day, a link's columns are read once per ~30 attempts, and what
+        // counts there is that the longest tiles of ALL links start first (Model 200 day 2.97 ms, by blocks 3.36).
+        int key_hi = 6;
+        static const int block_shift = [] {  // HLM_TUNE_COST_BLOCK_SHIFT (environment): for block-size experiments only
+            const char* e = std::getenv("HLM_TUNE_COST_BLOCK_SHIFT");
+            return e ? std::max(10, std::min(24, std::atoi(e))) : 15;
+        }();
+        a.cost_block_shift = block_shift;
+        a.cost_blocks = 1;
+        if (sorted_tiles && c->routed) {
+            a.cost_blocks = (int)((c->ns + (1LL << block_shift) - 1) >> block_shift);
+            for (int b = a.cost_blocks - 1; b > 0; b >>= 1) ++key_hi;
+        }
         const size_t n = (size_t)c->ns;
         HLM_CUDA(c->cost.reserve((size_t)c->ld));
-        // In routed runs the order is renewed every fourth launch: the sort is 46 us of a 1.1 ms coupling interval, and an
-        // order a few intervals old deals the links nearly as well (any permutation is a valid order; routed hour 4.60 ->
-        // 4.52 ms).  Unrouted launches are long (a day of Model 200: 5 ms) and their counts move more: every launch.
-        if (c->cost_ns == c->ns && (c->order_ns != c->ns || c->order_age >= ((c->routed && !sorted_tiles) ? 4 : 1))) {
+        // In routed runs the order serves several launches: the sort is 46 us (60 with the block bits) of a coupling
+        // interval of about a millisecond, and an order a few intervals old deals the links nearly as well (any
+        // permutation is a valid order).  Lane refill: every fourth launch (routed hour 4.60 -> 4.52 ms); sorted tiles,
+        // which depend on the counts being right: every second (3.72 -> 3.62 ms; every third or fourth 3.63).
+        // Unrouted launches are long (a day of Model 200) and their counts move more: every launch.
+        static const int age_tune = [] {  // HLM_TUNE_SORT_AGE (environment): launches per order, for experiments only
+            const char* e = std::getenv("HLM_TUNE_SORT_AGE");
+            return e ? std::max(1, std::atoi(e)) : 0;
+        }();
+        const int max_age = age_tune ? age_tune : (c->routed ? (sorted_tiles ? 2 : 4) : 1);
+        if (c->cost_ns == c->ns && (c->order_ns != c->ns || c->order_age >= max_age)) {
             HLM_CUDA(c->cost_sorted.reserve(n));
             HLM_CUDA(c->order.reserve(n));
             if (c->iota.cap < n) {
@@ -460,11 +485,11 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
             }
             size_t tmp_bytes = 0;
             HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
-                                                               (int)n, key_lo, 6, c->stream));
+                                                               (int)n, key_lo, key_hi, c->stream));
             HLM_CUDA(c->sort_tmp.reserve(tmp_bytes));
             HLM_CUDA(cub::DeviceRadixSort::SortPairsDescending(c->sort_tmp.p, tmp_bytes, c->cost.p, c->cost_sorted.p, c->iota.p, c->order.p,
-                                                               (int)n, key_lo, 6, c->stream));
-            c->launches += 3;  // histogram, scan, one scatter pass
+                                                               (int)n, key_lo, key_hi, c->stream));
+            c->launches += 2 + (key_hi - key_lo + 7) / 8;  // histogram, scan, one scatter pass per 8 key bits
             c->order_ns = c->ns;
             c->order_age = 0;
         }

@@ -175,6 +175,10 @@ struct WindowArgs {
     // of short ones; `cost` (or nullptr) receives the attempts each link takes in this launch.
     const int* order;        // [links of the launch] link indices
     int* cost;               // [ld]
+    // sorted tiles: the key a link leaves in `cost` carries, above its 6 bits of attempts, the number of its block of
+    // 2^cost_block_shift consecutive links counted from the END (cost_blocks - 1 - block), so that one descending sort
+    // lists the blocks in ascending order and, inside a block, the links by attempts; cost_blocks <= 1: attempts only
+    int cost_block_shift, cost_blocks;
     unsigned int* tile_counter;
     // routed models (Model::HAS_INFLOW): discharge entering each link from upstream, constant over the
     // interval (nullptr = unrouted, 0); and, for links another rank needs, where the epilogue puts the
@@ -467,6 +471,11 @@ __device__ __forceinline__ int cost_key(unsigned int attempts) {
     return (int)(k < 63u ? k : 63u);
 }
 
+__device__ __forceinline__ int cost_word(const WindowArgs& a, long long sys, unsigned int attempts) {
+    const int key = cost_key(attempts);
+    return a.cost_blocks > 1 ? (((a.cost_blocks - 1 - (int)(sys >> a.cost_block_shift)) << 6) | key) : key;
+}
+
 // Tile schedule: a warp takes 32 consecutive links and stays with them until the slowest lane leaves.  Right
 // when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
 // threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
@@ -551,7 +560,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
-            if (a.cost != nullptr) a.cost[sys] = cost_key(n_acc + n_rej + n_jmp - n_at_load);  // the next launch's sort key
+            if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load);  // the next launch's sort key
             if (status != kActive) route_publish(a, sys, (double)y[0]);
         }
     }
@@ -744,7 +753,7 @@ template <class Model, typename T> struct LinkRun {
         a.n_accept[sys] = n_acc;
         a.n_reject[sys] = n_rej;
         a.n_jump[sys] = n_jmp;
-        if (a.cost != nullptr) a.cost[sys] = cost_key(n_acc + n_rej + n_jmp - n_at_load);  // the sort reads 6 bits
+        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load);  // the sort reads 6 bits
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
@@ -854,7 +863,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45
             if (r.status == kActive) {
                 have = true;
             } else {
-                if (a.cost != nullptr) a.cost[r.sys] = 0;
+                if (a.cost != nullptr) a.cost[r.sys] = cost_word(a, r.sys, 0u);
                 dense_zero(a, r.sys, a.q_lo, a.q_hi);
             }
         }
@@ -916,7 +925,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45
                     if (r.status == kActive) {
                         have = true;
                     } else {
-                        if (a.cost != nullptr) a.cost[sys] = 0;
+                        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, 0u);
                         dense_zero(a, sys, a.q_lo, a.q_hi);
                     }
                 }
