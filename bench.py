@@ -65,7 +65,8 @@ def parse_args():
                     help="routed: boundary discharge all-gathered over NCCL, or stored into every rank's halo vector by the "
                          "kernels themselves (CUDA IPC peer memory) with a one-element all-reduce as the barrier")
     ap.add_argument("--schedule", default="auto", choices=["auto", "tiles", "lanes", "sorted"],
-                    help="how links are dealt to lanes (hlm_set_schedule); auto = lanes for routed runs, tiles otherwise")
+                    help="how links are dealt to lanes (hlm_set_schedule); auto = sorted tiles (tiles of links with equal attempt counts "
+                         "in the previous launch) for Model 200 and routed runs, plain tiles otherwise")
     ap.add_argument("--days", type=int, default=365, help="length of the forcing record / run horizon")
     ap.add_argument("--wet-fraction", type=float, default=0.0,
                     help="share of links started with surface storage so Model204's pow() branch runs")
@@ -458,7 +459,8 @@ def routed_record(env, args, K, W, links_per_gpu, with_e2e=True):
         "e2e": e2e, "gpu_launches": int(launches_all),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp_peak, "unit": "TFLOP/s", "frac": achieved / fp_peak,
                      "traffic": None, "flop_per_attempt": W_MIN_FLOP_PER_ATTEMPT_200, "attempts_per_launch": att_per_launch,
-                     "kernel_ms_avg": kern_avg_ms, "kernel": "hlm::rk45_lanes_kernel<Model200,double,true>",
+                     "kernel_ms_avg": kern_avg_ms, "kernel": ("hlm::rk45_lanes_kernel<Model200,double,true>" if args.schedule == "lanes" else
+                                "hlm::rk45_window_kernel<Model200,double> over sorted tiles (the first interval: rk45_lanes_kernel)"),
                      "kernel_share_of_step": kern_ms_all / max(world, 1) / ms_max,
                      "peak_source": "measured live (hlm_measure_fma_peak)"},
         "cpu_baseline": None, "clocks": clocks,
@@ -650,7 +652,7 @@ def model200_record(env, args, K, W):
     return {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K, "steps": K, "links": ns, "days_of_forcing": days,
             "attempts_per_accepted": r["attempts"] / max(r["acc"], 1.0), "accepted_steps_per_step": r["acc"] / K,
             "link_status_after_run": r["state"], "roofline_frac": roof["frac"], "kernel_ms_avg": roof["kernel_ms_avg"],
-            "schedule": "lanes (auto)", "note": "Model 200 is project-defined (the reference names it, README.md:95, and ships no "
+            "schedule": "sorted tiles (auto)", "note": "Model 200 is project-defined (the reference names it, README.md:95, and ships no "
             "definition): parity unpinned; one step = one simulated day, hourly dense output, implicit fallback on"}
 
 

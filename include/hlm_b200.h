@@ -141,7 +141,9 @@ int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
  * is done — right when neighbouring links step alike (links sorted by forcing cell).  LANES: a lane takes the
  * next unclaimed link the moment it is done with its own, so a warp never idles behind its slowest link —
  * right when links take unlike numbers of attempts per launch (routed runs with short coupling intervals).
- * AUTO (default): LANES for Model 200 and for routed runs, TILES otherwise.  Results are bit-identical under either. */
+ * AUTO (default): SORTED_TILES (below) for Model 200 and for routed runs, falling back to LANES for a launch that has no
+ * attempt counts to sort by yet (the first one, or one over part of the links); TILES otherwise.  Results are
+ * bit-identical under every schedule. */
 #define HLM_SCHEDULE_AUTO 0
 #define HLM_SCHEDULE_TILES 1
 #define HLM_SCHEDULE_LANES 2

@@ -166,7 +166,7 @@ class Context {
     /// Links the RK45 path flags stiff are carried on by the Radau IIA fallback (run_rk45's documented
     /// behaviour, solver/rk45_api.hpp:198-247) instead of being abandoned; they come back as HLM_LINK_STIFF_SOLVED.
     void setStiffFallback(bool on) { check(hlm_set_stiff_fallback(ctx_, on ? 1 : 0), "hlm_set_stiff_fallback"); }
-    /// HLM_SCHEDULE_AUTO / _TILES / _LANES: how links are dealt to lanes (bit-identical results either way).
+    /// HLM_SCHEDULE_AUTO / _TILES / _LANES / _SORTED_TILES: how links are dealt to lanes (bit-identical results either way).
     void setSchedule(int mode) { check(hlm_set_schedule(ctx_, mode), "hlm_set_schedule"); }
 
     struct Result {

@@ -101,19 +101,6 @@ struct Model204 {
             recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
         }
         __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + wet_slot(c)); }
-        // The same load from values staged ahead of time (lane schedule, rk45_lanes_kernel): v[i] = column staged_col(i).
-        static constexpr int N_STAGED = 11;
-        static __host__ __device__ constexpr int staged_col(int i) {
-            constexpr int c[N_STAGED] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, MELT_F, TEMP_THR, R_HU, R_ALPHA3, R_ALPHA4, R_A_H};
-            return c[i];
-        }
-        __device__ __forceinline__ void load_staged(const double (&v)[N_STAGED], const double* __restrict__ sp, long long ld_, long long sys) {
-#pragma unroll
-            for (int i = 0; i < 10; ++i) p[staged_col(i)] = (T)v[i];
-            wet = sp + (long long)N_SP * ld_ + sys * kWetStride;
-            const double ra = v[10];
-            recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
-        }
     };
 
     /// true when every hoisted reciprocal is usable (divisors inside div_recip's exponent range)
@@ -291,20 +278,6 @@ struct Model200 {
         }
         __device__ __forceinline__ void set_inflow(T v) { qin = v; }
         __device__ __forceinline__ T wet_param(int c) const { return (T)__ldg(wet + wet_slot(c)); }
-        // staged load, as Model204::Link
-        static constexpr int N_STAGED = 11;
-        static __host__ __device__ constexpr int staged_col(int i) {
-            constexpr int c[N_STAGED] = {INFIL, PERCO, HU, ALPHA3, ALPHA4, CH, INVTAU, R_HU, R_ALPHA3, R_ALPHA4, R_A_H};
-            return c[i];
-        }
-        __device__ __forceinline__ void load_staged(const double (&v)[N_STAGED], const double* __restrict__ sp, long long ld_, long long sys) {
-#pragma unroll
-            for (int i = 0; i < 10; ++i) p[staged_col(i)] = (T)v[i];
-            wet = sp + (long long)N_SP * ld_ + sys * kWetStride;
-            qin = (T)0;
-            const double ra = v[10];
-            recips_ok = p[R_HU] == p[R_HU] && ra == ra && p[R_ALPHA3] == p[R_ALPHA3] && p[R_ALPHA4] == p[R_ALPHA4];
-        }
     };
 
     template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>& P) { return P.recips_ok; }
@@ -381,8 +354,6 @@ struct DummyModel {
     static __device__ __forceinline__ void prepare_wet(const double*, double*) {}
     template <typename T> struct Link {
         __device__ __forceinline__ void load(const double*, long long, long long) {}
-        static constexpr int N_STAGED = 0;
-        static __host__ __device__ constexpr int staged_col(int) { return 0; }
     };
     template <typename T> static __device__ __forceinline__ bool fast_div_ok(const Link<T>&) { return true; }
     template <typename T, bool kFast, typename G>

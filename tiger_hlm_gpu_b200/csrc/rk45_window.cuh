@@ -585,51 +585,6 @@ template <typename T> struct RunConsts {
     }
 };
 
-// ---- staging of a lane's NEXT link (lane schedule) ---------------------------------------------------------------
-// A lane's loads are its own — ~25 columns at one index, nothing coalesced — and a lane that waits for them holds up
-// its warp: with 3.4 attempts per link (routed runs) some lane of a warp changes link in almost every pass, and the
-// capture of the refill kernel showed 2.9 cycles of long-scoreboard stall per issued instruction, the FP64 pipe at 35 %.
-// So the columns of the link a lane will take NEXT are copied into the lane's own shared-memory slots by cp.async
-// while it integrates the current one (no registers, no scoreboard), and taking a link is 25 shared-memory loads.
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <class Model> struct LaneStage {
-    static constexpr int N8 = Model::N_EQ + 2 + Model::template Link<double>::N_STAGED + (Model::HAS_INFLOW ? 1 : 0);
-    static constexpr int N4 = 7;
-};
-// slot order = the order LinkRun::load_staged reads them in
-template <class Model>
-__device__ __forceinline__ void stage_link(const WindowArgs& a, long long sys, double* s8, int* s4) {
-    constexpr int TH = HLM_CTA_THREADS;
-    constexpr int N = Model::N_EQ;
-    constexpr int NP = Model::template Link<double>::N_STAGED;
-#pragma unroll
-    for (int i = 0; i < N; ++i) cp_async8(s8 + i * TH, a.y + (long long)i * a.ld + sys);
-    cp_async8(s8 + N * TH, a.t + sys);
-    cp_async8(s8 + (N + 1) * TH, a.h + sys);
-#pragma unroll
-    for (int j = 0; j < NP; ++j)
-        cp_async8(s8 + (N + 2 + j) * TH, a.sp + (long long)Model::template Link<double>::staged_col(j) * a.ld + sys);
-    if constexpr (Model::HAS_INFLOW) {
-        if (a.qin != nullptr) cp_async8(s8 + (N + 2 + NP) * TH, a.qin + sys);
-    }
-    cp_async4(s4 + 0 * TH, a.next_q + sys);
-    cp_async4(s4 + 1 * TH, a.reject_run + sys);
-    cp_async4(s4 + 2 * TH, a.status + sys);
-    cp_async4(s4 + 3 * TH, a.n_accept + sys);
-    cp_async4(s4 + 4 * TH, a.n_reject + sys);
-    cp_async4(s4 + 5 * TH, a.n_jump + sys);
-    if (Model::N_FORC > 0 && a.n_forc > 0 && a.col != nullptr) cp_async4(s4 + 6 * TH, a.col + sys);
-    cp_async_commit();
-}
-
 // One link's integration state, held in registers by its lane: load() / attempt() ... / store().
 // attempt() is one pass of the reference's loop body (rk45_kernel.cu:53-164) and returns true when the lane
 // leaves the link: integrated to tf, paused at the window's end, out of attempts, or flagged stiff.
@@ -663,36 +618,6 @@ template <class Model, typename T> struct LinkRun {
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
         col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
-        finish_load(a);
-    }
-
-    // The same load from the lane's staging columns in shared memory (stage_link put them there while the lane was
-    // integrating its previous link): s8[k * HLM_CTA_THREADS] = 8-byte slot k, s4[k * HLM_CTA_THREADS] = 4-byte slot k.
-    __device__ __forceinline__ void load_staged(const WindowArgs& a, long long sys_, const double* s8, const int* s4) {
-        constexpr int TH = HLM_CTA_THREADS;
-        constexpr int NP = Model::template Link<T>::N_STAGED;
-        sys = sys_;
-#pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = (T)s8[i * TH];
-        t = (T)s8[N * TH];
-        h = (T)s8[(N + 1) * TH];
-        next_q = s4[0 * TH];
-        reject_run = s4[1 * TH];
-        status = s4[2 * TH];
-        n_acc = (unsigned int)s4[3 * TH];
-        n_rej = (unsigned int)s4[4 * TH];
-        n_jmp = (unsigned int)s4[5 * TH];
-        n_at_load = n_acc + n_rej + n_jmp;
-        if constexpr (NP > 0) {
-            double v[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) v[j] = s8[(N + 2 + j) * TH];
-            L.load_staged(v, a.sp, a.ld, sys);
-        } else {
-            L.load(a.sp, a.ld, sys);
-        }
-        if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)s8[(N + 2 + NP) * TH] : (T)0);
-        col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)s4[6 * TH] : sys) : 0;
         finish_load(a);
     }
 
@@ -773,124 +698,9 @@ template <class Model, typename T> struct LinkRun {
 // LinkRun::finished).  Worth it when links take few attempts per launch (routed runs: +10 %); with tens of
 // attempts per link the larger register footprint of the merged control flow costs more than the idle pass
 // (unrouted Model 200: -10 %), so the launcher picks.
-// HLM_LANES_STAGED=1: the experiment of staging a lane's next link in shared memory (below).  Measured on the routed
-// hour (2.5 M links, 15-minute intervals: lane kernel per interval) and on Model 200 unrouted (1 M links, per day),
-// profiles/r2u_ab_lanes_staged.log:
-//                                   3 CTAs/SM (168 registers)      2 CTAs/SM (250 registers, no spills)
-//   refill on demand (the default)  1.335 ms / 6.68 ms             1.424 / 7.01
-//   staged                          1.654 / 9.58                   1.396 / 6.51
-// At 3 CTAs/SM the 69 KB of staging slots come out of the L1 the kernel's 850 bytes of spills per thread live in
-// (DRAM traffic of a launch 1.9 -> 6.7 GB); at 2 CTAs/SM nothing spills and staging does pay (2-7 %), but two warps
-// per scheduler lose more than that.  Dealing the positions to the lanes statically instead of claiming them
-// (no atomics at all) was worse still: 2.35 ms, the per-lane totals are too uneven.  Kept for the record, off.
-#ifndef HLM_LANES_STAGED
-#define HLM_LANES_STAGED 0
-#endif
-#if HLM_LANES_STAGED
-#ifndef HLM_LANES_CHUNK
-#define HLM_LANES_CHUNK 256
-#endif
-// Lane refill with everything a link needs in place before the lane turns to it.  Three links are in a lane's hands:
-// the one it integrates; the one whose columns are staged in its shared-memory slots (stage_link, issued when the lane
-// took the current one); and the one after, of which it holds the index (`after`: the load of a.order[position] issued
-// at the same moment).  Positions of the launch's order (most attempts first) are claimed per warp in chunks of
-// HLM_LANES_CHUNK with one global atomicAdd by lane 0 when the warp's pool runs low — in converged code at the top of a
-// pass, once per few hundred links — and dealt to the lanes from the pool by shared-memory atomics, so no lane waits
-// for L2 or DRAM between two links (the refill-on-demand version, HLM_LANES_STAGED=0, waited four times in series: the
-// warp's atomicAdd, a.order, the columns, the forcing sample).
-template <class Model, typename T, bool kEarlyLeave>
-__global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45_lanes_kernel(const WindowArgs a) {
-    const unsigned int lane = threadIdx.x & 31;
-    const long long first = a.tile_lo << 5;
-    const long long last = ((a.tile_lo + a.n_tiles) << 5) < a.ns ? ((a.tile_lo + a.n_tiles) << 5) : a.ns;
-    const long long n_links = last - first;
-    const RunConsts<T> c(a);
-    HLM_K_SHARED_DECL(T, Model::N_EQ);
-    __shared__ double stage8[LaneStage<Model>::N8][HLM_CTA_THREADS];
-    __shared__ int stage4[LaneStage<Model>::N4][HLM_CTA_THREADS];
-    // the warp's pool of claimed positions: two ranges [next, end), the second one the chunk claimed ahead
-    __shared__ int pool_all[HLM_CTA_THREADS / 32][4];
-    double* const s8 = &stage8[0][threadIdx.x];
-    int* const s4 = &stage4[0][threadIdx.x];
-    int* const pool = pool_all[threadIdx.x >> 5];
-    if (lane == 0) pool[0] = pool[1] = pool[2] = pool[3] = 0;
-    __syncwarp();
-    LinkRun<Model, T> r;
-    r.k.bind(HLM_K_SHARED_BASE);
-    auto link_at = [&](long long p) -> long long { return a.order != nullptr ? (long long)__ldg(a.order + p) : first + p; };
-    long long staged = -1, after = -1;
-    bool have = false, global_dry = false;  // global_dry: lane 0's note that the launch's counter has run past the end
-    for (;;) {
-        // ---- converged: keep at least a pass's worth of positions in the pool ----
-        int left = 0;
-        __syncwarp();
-        if (lane == 0) {
-            int n1 = pool[0], e1 = pool[1];
-            if (n1 >= e1) {  // first range used up: the chunk claimed ahead moves in
-                n1 = pool[2];
-                e1 = pool[3];
-                pool[0] = n1;
-                pool[1] = e1;
-                pool[2] = pool[3] = 0;
-            }
-            int n2 = pool[2], e2 = pool[3];
-            if (n2 >= e2 && e1 - n1 < 32 && !global_dry) {
-                const unsigned int b = atomicAdd(a.tile_counter, (unsigned int)HLM_LANES_CHUNK);
-                if ((long long)b >= n_links) {
-                    global_dry = true;
-                } else {
-                    n2 = (int)b;
-                    e2 = (int)(((long long)b + HLM_LANES_CHUNK < n_links) ? (long long)b + HLM_LANES_CHUNK : n_links);
-                    if (n1 >= e1) {
-                        pool[0] = n1 = n2;
-                        pool[1] = e1 = e2;
-                        n2 = e2 = 0;
-                    } else {
-                        pool[2] = n2;
-                        pool[3] = e2;
-                    }
-                }
-            }
-            left = (e1 > n1 ? e1 - n1 : 0) + (e2 > n2 ? e2 - n2 : 0);
-        }
-        __syncwarp();  // lane 0's pool writes before the takes below
-        left = __shfl_sync(0xffffffffu, left, 0);
-        // ---- per lane: take the staged link, stage the one after, draw the index of the one after that ----
-        if (!have && staged >= 0) {
-            cp_async_wait_all();
-            r.load_staged(a, staged, s8, s4);
-            staged = -1;
-            if (r.status == kActive) {
-                have = true;
-            } else {
-                if (a.cost != nullptr) a.cost[r.sys] = cost_word(a, r.sys, 0u);
-                dense_zero(a, r.sys, a.q_lo, a.q_hi);
-            }
-        }
-        if (staged < 0 && after >= 0) {
-            staged = after;
-            after = -1;
-            stage_link<Model>(a, staged, s8, s4);
-        }
-        if (after < 0 && left > 0) {
-            int p = atomicAdd(&pool[0], 1);
-            if (p >= pool[1]) {
-                p = atomicAdd(&pool[2], 1);
-                if (p >= pool[3]) p = -1;
-            }
-            if (p >= 0) after = link_at(p);
-        }
-        if (__ballot_sync(0xffffffffu, have) == 0u) {
-            if (left == 0 && __ballot_sync(0xffffffffu, staged >= 0 || after >= 0) == 0u) break;
-            continue;
-        }
-        if (have && (r.attempt(a, c) || (kEarlyLeave && r.finished(a, c)))) {
-            r.store(a);
-            have = false;
-        }
-    }
-}
-#else
+// (Experiments on this kernel that were measured and not kept — the next link's columns staged in shared memory by
+// cp.async, positions dealt statically, claims and order lookups two passes ahead through a per-warp ring with L2
+// prefetch — are in DESIGN.md section 5 with their logs under profiles/; commit 2f565ba holds the staged version.)
 template <class Model, typename T, bool kEarlyLeave>
 __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45_lanes_kernel(const WindowArgs a) {
     const unsigned int lane = threadIdx.x & 31;
@@ -942,6 +752,5 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45
     }
 }
 
-#endif  // HLM_LANES_STAGED
 
 }  // namespace hlm
