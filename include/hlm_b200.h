@@ -126,7 +126,8 @@ int hlm_set_max_attempts(hlm_ctx* ctx, long long per_link);
  * model's min/max terms the error estimate falls like h, not h^5, and the controller needs a run of 6-8 rejections
  * to get past — not stiffness.  Routed runs, where one abandoned link starves everything downstream and the
  * implicit fallback costs a serial chain of Newton solves per interval, raise it (20) and leave true stiffness to
- * the other test, h < (tf - t0) * 1e-6. */
+ * the other test, h < (tf - t0) * 1e-6; so do the drivers for unrouted Model 200 runs (hlm_run, bench.py), whose first
+ * day otherwise hands 1.5 % of the links to the fallback for seconds. */
 int hlm_set_reject_limit(hlm_ctx* ctx, int n);
 /* Bytes of device memory one dense-output window buffer may take (two are allocated when the run
  * needs more than one window).  Default 8 GiB. */
