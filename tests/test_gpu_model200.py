@@ -54,6 +54,46 @@ def test_model200_unrouted_equals_oracle_bit_for_bit(solver, ns):
         assert np.array_equal(g[k], o[k]), k
 
 
+def test_model200_days_in_a_resident_session_under_every_schedule(solver):
+    """Three day-sized intervals chained on the device (hlm_solve_restart: what chained run_rk45 calls do).  From the
+    second day on AUTO deals the links as sorted tiles — 32 links that took the same number of attempts the day
+    before — over all links (unrouted: no blocks); the first day, and the "lanes"/"tiles" runs, take the other kernels.
+    Same arithmetic per link: the same bits as the CPU oracle chained the same way."""
+    ns, days = 3000, 3
+    sp, col, pr, t2m, y0 = inputs(ns, days=days, seed=5)
+    F = O.Forcing([pr, t2m], [1.0, 24.0], col=col)
+    y, acc_o, dense_o = y0, np.zeros(ns, np.int64), []
+    for d in range(days):
+        tq = synthetic.hourly_queries(d * 1440.0, (d + 1) * 1440.0)
+        o = O.run_rk45(200, OPRM, y, d * 1440.0, (d + 1) * 1440.0, tq, sp=sp, forcing=F, device_pow=True, threads=8,
+                       max_attempts=2_000_000, reject_limit=routing.ROUTED_REJECT_LIMIT)
+        assert (o["stiff"] == 0).all()  # (with the reference's limit of 5 the first day's kinks flag a few links)
+        y, acc_o = o["final"], acc_o + o["n_accept"]
+        dense_o.append(o["dense"])
+    upload(solver, sp, col, pr, t2m)
+    solver.route_clear()
+    try:
+        solver.set_reject_limit(routing.ROUTED_REJECT_LIMIT)
+        for schedule in ("auto", "sorted", "lanes", "tiles"):
+            solver.set_schedule(schedule)
+            for d in range(days):
+                tq = synthetic.hourly_queries(d * 1440.0, (d + 1) * 1440.0)
+                if d == 0:
+                    solver.solve_begin(200, y0, 0.0, 1440.0, tq)
+                else:
+                    solver.solve_restart(d * 1440.0, (d + 1) * 1440.0, tq)
+                solver.solve_window(len(tq), True)
+                win = np.zeros((ns, len(tq), 5))
+                solver.solve_wait_copy(solver.solve_fetch_window_packed(win))
+                assert np.array_equal(win, dense_o[d]), (schedule, d)
+            r = solver.solve_end()
+            assert np.array_equal(r["final"], y), schedule
+            assert np.array_equal(r["n_accept"], acc_o), schedule
+    finally:
+        solver.set_schedule("auto")
+        solver.set_reject_limit(5)
+
+
 def test_model200_fp32_mode_close_to_fp64(solver):
     sp, col, pr, t2m, y0 = inputs(256)
     upload(solver, sp, col, pr, t2m)
