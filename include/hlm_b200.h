@@ -148,8 +148,9 @@ int hlm_set_stiff_fallback(hlm_ctx* ctx, int enable);
 #define HLM_SCHEDULE_AUTO 0
 #define HLM_SCHEDULE_TILES 1
 #define HLM_SCHEDULE_LANES 2
-/* SORTED_TILES (models with an inflow term, i.e. Model 200; TILES otherwise): tiles of 32 links that took the SAME
- * number of attempts in the previous launch, whatever their indices — lockstep tiles where neighbouring links differ. */
+/* SORTED_TILES: tiles of 32 links that took the SAME number of attempts in the previous launch, whatever their
+ * indices — lockstep tiles where neighbouring links differ (FP64; a launch that has no counts to sort by yet, or covers
+ * part of the links, takes LANES).  For a Model204 data set whose neighbouring links do not step alike. */
 #define HLM_SCHEDULE_SORTED_TILES 3
 int hlm_set_schedule(hlm_ctx* ctx, int mode);
 /* 64 (default, the reference's arithmetic) or 32 (FP32 state/stages; no reference counterpart). */

@@ -233,6 +233,38 @@ def test_lane_refill_schedule_is_bit_identical_to_tiles(solver, golden_dummy):
     solver.set_model_parameters(204, PRM)
 
 
+def test_sorted_tiles_schedule_is_bit_identical_to_tiles(solver):
+    """HLM_SCHEDULE_SORTED_TILES for a model without an inflow term (its second tile-kernel instance): three days chained
+    in a resident session — the first launch has no attempt counts to sort by and takes lane refill, the next two run as
+    tiles of links with equal counts — give the bits of the plain tile schedule, dense records and counters included."""
+    ns, days = 2500, 3
+    sp, y0, forcing = setup_synth(solver, ns, days, wet_fraction=0.4)
+    runs = {}
+    try:
+        for schedule in ("tiles", "sorted"):
+            solver.set_schedule(schedule)
+            dense = []
+            for d in range(days):
+                tq = synthetic.hourly_queries(d * 1440.0, (d + 1) * 1440.0)
+                if d == 0:
+                    solver.solve_begin(204, y0, 0.0, 1440.0, tq)
+                else:
+                    solver.solve_restart(d * 1440.0, (d + 1) * 1440.0, tq)
+                solver.solve_window(len(tq), True)
+                win = np.zeros((ns, len(tq), 5))
+                solver.solve_wait_copy(solver.solve_fetch_window_packed(win))
+                dense.append(win)
+            r = solver.solve_end()
+            r["dense"] = np.concatenate(dense, axis=1)
+            runs[schedule] = r
+    finally:
+        solver.set_schedule("auto")
+    a, b = runs["tiles"], runs["sorted"]
+    assert a["n_accept"].sum() > 100 * ns
+    for k in ("final", "dense", "stiff", "n_accept", "n_reject", "n_jump"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_windows_with_steps_longer_than_the_query_spacing(solver, golden_dummy):
     """DummyModel takes 12 steps for 10 000 queries: every window boundary falls inside a step, which
     exercises the leave-uncommitted-and-redo path."""

@@ -429,12 +429,13 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     else return fail(HLM_ERR_INVALID, "unknown model uid");
     // Which schedule.  Where links take unlike numbers of attempts per launch (Model 200, every routed run) AUTO asks
     // for sorted tiles — tiles of 32 links that took the same number of attempts in the previous launch — when the model's
-    // kernel can follow an order (the ones with an inflow term) and there is one (from the second launch over all links
-    // on); a launch without an order goes to lane refill, which also records the counts the next launch is sorted by.
+    // run can change its schedule freely (the models with an inflow term: project-defined) and there is an order (from
+    // the second launch over all links on); a launch without an order goes to lane refill, which also records the counts
+    // the next launch is sorted by.  Any model takes sorted tiles when asked (HLM_SCHEDULE_SORTED_TILES).
     const bool has_inflow = c->uid == hlm::Model200::UID;
     const bool divergent = c->routed || divergent_model;
     const bool lanes_asked = c->schedule == HLM_SCHEDULE_LANES || (c->schedule == HLM_SCHEDULE_AUTO && divergent);
-    const bool sorted_tiles = has_inflow && !f32 && (c->schedule == HLM_SCHEDULE_SORTED_TILES || (c->schedule == HLM_SCHEDULE_AUTO && divergent));
+    const bool sorted_tiles = !f32 && (c->schedule == HLM_SCHEDULE_SORTED_TILES || (has_inflow && c->schedule == HLM_SCHEDULE_AUTO && divergent));
     hlm::WindowArgs a = a_in;
     // Longest first.  Under lane refill a launch ends with the lanes that drew a long link late while the others have
     // run out of links (22 of 32 threads active on the routed workload).  A link's attempt count changes slowly from
@@ -513,7 +514,7 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     // routed runs take a few attempts per link per launch: the lane kernel that tests for "finished" right
     // after the attempt (rk45_window.cuh, kEarlyLeave)
     const bool lanes = (lanes_asked || sorted_tiles) && !(sorted_tiles && a.order != nullptr);
-    HLM_CUDA(launch(lanes ? (c->routed ? 2 : 1) : 0, a, c->sm_count, c->stream));
+    HLM_CUDA(launch(lanes ? (c->routed ? 2 : 1) : ((sorted_tiles && a.order != nullptr) ? 3 : 0), a, c->sm_count, c->stream));
     HLM_CUDA(cudaEventRecord(e1, c->stream));
     c->timing.emplace_back(e0, e1);
     ++c->launches;

@@ -13,13 +13,17 @@
 namespace hlm {
 
 // schedule 0: tiles (rk45_window_kernel); 1: lane refill; 2: lane refill with the early-leave test (few attempts
-// per link per launch).  The grid is SMs x resident CTAs of the kernel (persistent warps pull work from a
+// per link per launch); 3: tiles taken from the launch's order (sorted tiles).  The grid is SMs x resident CTAs of the kernel (persistent warps pull work from a
 // counter), fewer when there is less work.
 // a template so that `if constexpr` really leaves the kernels an instance does not carry uninstantiated
 template <class Model, typename T>
 static cudaError_t launch_rk45_impl(int schedule, const WindowArgs& a, int sm_count, cudaStream_t stream) {
-    static int blocks_per_sm[3] = {0, 0, 0};
-    if (schedule < 0 || schedule > 2) return cudaErrorInvalidValue;
+    static int blocks_per_sm[4] = {0, 0, 0, 0};
+    if (schedule < 0 || schedule > 3) return cudaErrorInvalidValue;
+    // schedule 3: the tile kernel that follows the launch's order (sorted tiles).  Models with an inflow term have it as
+    // their only tile kernel; the others carry it as a second FP64 instance beside the plain one.
+    constexpr bool kHasSortedInstance = sizeof(T) == 8 && !Model::HAS_INFLOW;
+    if (schedule == 3 && !kHasSortedInstance) schedule = 0;
     // Which kernels this instance carries (each is minutes of ptxas): lane refill for FP64 only — FP32 has no
     // routed use (the implicit fallback is FP64) — and its early-leave variant for the models routed runs use
     // (those with an inflow term).  A schedule the instance lacks falls back to the next simpler one.
@@ -46,6 +50,11 @@ static cudaError_t launch_rk45_impl(int schedule, const WindowArgs& a, int sm_co
     if (schedule == 0) {
         if (cudaError_t e = occupancy(rk45_window_kernel<Model, T>, 0)) return e;
         rk45_window_kernel<Model, T><<<grid_for(blocks_per_sm[0]), HLM_CTA_THREADS, 0, stream>>>(a);
+    } else if (schedule == 3) {
+        if constexpr (kHasSortedInstance) {
+            if (cudaError_t e = occupancy(rk45_window_kernel<Model, T, true>, 3)) return e;
+            rk45_window_kernel<Model, T, true><<<grid_for(blocks_per_sm[3]), HLM_CTA_THREADS, 0, stream>>>(a);
+        }
     } else if (schedule == 1) {
         if constexpr (kHasLanes) {
             if (cudaError_t e = occupancy(rk45_lanes_kernel<Model, T, false>, 1)) return e;

@@ -479,7 +479,10 @@ __device__ __forceinline__ int cost_word(const WindowArgs& a, long long sys, uns
 // Tile schedule: a warp takes 32 consecutive links and stays with them until the slowest lane leaves.  Right
 // when the lanes of a tile run in lockstep (links sorted by forcing cell with like parameters: 31.9 of 32
 // threads active per instruction on the Model204 workload).  The other schedule is rk45_lanes_kernel below.
-template <class Model, typename T>
+// kFollowOrder: the kernel can take its tiles from the launch's order (sorted tiles) and records the sort key.  Always
+// for the models routed runs use; for the others a second instance, so that the plain one — the bench's hot kernel —
+// keeps its instructions and registers exactly.
+template <class Model, typename T, bool kFollowOrder = Model::HAS_INFLOW>
 __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_PER_SM_F32 : HLM_BLOCKS_PER_SM) rk45_window_kernel(const WindowArgs a) {
     using f = fp<T>;
     constexpr int N = Model::N_EQ;
@@ -500,10 +503,10 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         if ((long long)tile >= n_tiles) break;
         long long sys = ((a.tile_lo + (long long)tile) << 5) + lane;
         if (sys >= a.ns) continue;
-        // Sorted tiles (models with an inflow term, i.e. the ones routed runs use): the tile is 32 consecutive entries of
+        // Sorted tiles: the tile is 32 consecutive entries of
         // the launch's order — links that took the same number of attempts in the previous launch — instead of 32
         // consecutive links, so its lanes finish together although neighbouring links do not.
-        if constexpr (Model::HAS_INFLOW) {
+        if constexpr (kFollowOrder) {
             if (a.order != nullptr) sys = (long long)__ldg(a.order + (sys - (a.tile_lo << 5)));
         }
         int status = a.status[sys];
@@ -559,8 +562,10 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         a.n_jump[sys] = n_jmp;
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
-        if constexpr (Model::HAS_INFLOW) {
+        if constexpr (kFollowOrder) {
             if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load);  // the next launch's sort key
+        }
+        if constexpr (Model::HAS_INFLOW) {
             if (status != kActive) route_publish(a, sys, (double)y[0]);
         }
     }
