@@ -6,8 +6,11 @@
 //
 // Same per-link algorithm, same FP operations in the same order (see fp_exact.cuh), different
 // machine mapping:
-//   * one lane per link, one warp per tile of 32 consecutive links, persistent warps that pull
-//     tiles from an atomic counter — no __syncthreads anywhere, grid = SMs x resident CTAs;
+//   * one lane per link, one warp per tile of 32 links, persistent warps that pull tiles from an
+//     atomic counter — no __syncthreads anywhere, grid = SMs x resident CTAs.  A tile is 32
+//     consecutive links where neighbours step alike, and 32 links that took the same number of
+//     attempts in the previous launch where they do not (sorted tiles: Model 200, routed runs);
+//     lane refill (rk45_lanes_kernel) serves the launches that have no counts to sort by;
 //   * state, per-link parameters and counters are structure-of-arrays: every load/store of a tile
 //     is one coalesced 256-byte line per column;
 //   * all seven stage slopes, the state and the link parameters stay in registers for the whole
