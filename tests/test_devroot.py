@@ -27,6 +27,22 @@ def test_roots_within_a_few_ulp_of_long_double_pow(which, num, den, bound):
     assert np.all(np.diff(O.eval_root(which, np.sort(x[:50_000]))) >= 0)  # monotone on the sample
 
 
+def test_roots_of_perfect_powers_and_binade_edges():
+    """x = n^5 and x = n^3 (exactly representable): the roots come back within 3 ulp of n and n^2; and the routines
+    cross binade edges of the argument without a jump (neighbouring doubles give results at most 2 ulp apart)."""
+    n = np.arange(1, 2000, dtype=np.float64)
+    r5 = O.eval_root(5, n ** 5)
+    r3 = O.eval_root(6, n ** 3)
+    assert np.max(np.abs(r5 - n) / np.spacing(n)) <= 3
+    assert np.max(np.abs(r3 - n * n) / np.spacing(n * n)) <= 3
+    for e in range(-40, 41, 3):
+        edge = 2.0 ** e
+        x = np.array([np.nextafter(edge, 0.0), edge, np.nextafter(edge, np.inf)])
+        for which in (5, 6):
+            r = O.eval_root(which, x)
+            assert np.all(np.abs(np.diff(r)) <= 2 * np.spacing(r[1])), (which, e)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", [5, 6])
 def test_device_roots_equal_the_c_twin_bit_for_bit(solver, which):
