@@ -414,10 +414,11 @@ cudaEvent_t get_event(hlm_ctx* c) {
     return e;
 }
 
-// One window launch.  Schedule: tiles (a warp stays with 32 consecutive links) or lane refill (rk45_window.cuh);
-// by default lanes where links take unlike numbers of attempts per launch — Model 200 (the channel's pace grows
-// with its discharge: 24 attempts per day at the median, 150 at the 99th percentile) and every routed run —
-// tiles otherwise.  The kernels live in rk45_instance.cu, one translation unit per (model, number type).
+// One window launch.  Schedule (rk45_window.cuh): tiles of 32 consecutive links; tiles of 32 links that took the same
+// number of attempts in the previous launch (sorted tiles); or lane refill.  By default plain tiles, and where links
+// take unlike numbers of attempts per launch — Model 200 (the channel's pace grows with its discharge: 24 attempts per
+// day at the median, 150 at the 99th percentile) and every routed run — sorted tiles, with lane refill for the launches
+// that have no counts to sort by.  The kernels live in rk45_instance.cu, one translation unit per (model, number type).
 int dispatch_window(hlm_ctx* c, const hlm::WindowArgs& a_in) {
     using Launcher = cudaError_t (*)(int, const hlm::WindowArgs&, int, cudaStream_t);
     Launcher launch = nullptr;
